@@ -1,0 +1,160 @@
+/*
+ * rbffd.h -- C ABI of librbffd.so: the B200 (sm_100a) implementation of the operator-generation and
+ * operator-application hot path of RadialBasisFiniteDifferences.jl.
+ *
+ * The reference has no FFI layer; its boundary is the exported Julia API
+ * (src/RadialBasisFiniteDifferences.jl:25-75).  Every entry point below names the reference call it
+ * replaces.  Julia reaches these with `ccall` (INTEGRATION.md shows the stubs); the Python mirror in
+ * radialbasisfinitedifferences.jl_b200/api.py binds exactly the same symbols with ctypes.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no C++/torch types.
+ *   - "_host" entry points take HOST buffers (the caller's Julia/NumPy arrays), do the H2D/D2H copies
+ *     themselves and block until the result is in the caller's buffers.
+ *   - "_device" entry points take DEVICE pointers on the context's device and are asynchronous on the
+ *     context's stream (rbffd_set_stream / rbffd_synchronize).
+ *   - node coordinates are interleaved FP64 (x0 y0 [z0] x1 y1 ...), i.e. pointer(X) of a
+ *     Vector{SVector{d,Float64}} (test/poisson_test.jl:21-22, src/extractcoordinates.jl:11).
+ *   - index arrays crossing the host boundary are int64 and use opts->index_base (Julia: 1).
+ *     Device index arrays are int32, 0-based.
+ *   - every operator row holds exactly n entries (zeros kept; src/generate_operator.jl:171-182), so the
+ *     CSR row pointer is implicit: rowptr[k] = k*n.  All operators of one call share `colind`.
+ *   - return value: 0 = ok, otherwise an rbffd_status; rbffd_last_error() gives the message.
+ *     There is no CPU fallback: without a CUDA device every compute call returns RBFFD_ERR_CUDA.
+ */
+#ifndef RBFFD_H
+#define RBFFD_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RBFFD_MAX_OPS 12
+#define RBFFD_MAX_DIM 3
+
+typedef enum {
+    RBFFD_OK = 0,
+    RBFFD_ERR_INVALID = 1,    /* bad argument (DimensionMismatch / ArgumentError in the reference)       */
+    RBFFD_ERR_K_TOO_LARGE = 2,/* n > number of visible points (ArgumentError from knn)                   */
+    RBFFD_ERR_SINGULAR = 3,   /* zero pivot (SingularException from inv, interpolationmatrix.jl:8)        */
+    RBFFD_ERR_CUDA = 4,       /* CUDA runtime failure, including "no device"                            */
+    RBFFD_ERR_UNSUPPORTED = 5 /* parameter outside the compiled range (e.g. even PHS power)              */
+} rbffd_status;
+
+/* operator kinds (ops[i][0]) */
+#define RBFFD_OP_DERIV 0    /* d^alpha with alpha = (ops[i][1], ops[i][2], ops[i][3]); weights are multiplied by
+                               s^alpha exactly as generate_operator.jl:161-166 / hyperviscosity_operator.jl:159-160 */
+#define RBFFD_OP_LAPLACE 1  /* Dxx+Dyy[+Dzz] from ONE right-hand side; extension, not in the reference */
+
+typedef struct {
+    int32_t dim;        /* 2 (reference) or 3 (extension)                                               */
+    int32_t p;          /* PHS power r^p, odd                         rbfbasis.jl:9                      */
+    int32_t polydeg;    /* augmented polynomial degree                polynomialbasis.jl:8               */
+    int32_t n;          /* stencil size                               generate_operator.jl:45            */
+    int32_t nops;       /* number of operators (right-hand sides) per row, <= RBFFD_MAX_OPS              */
+    int32_t ops[RBFFD_MAX_OPS][4];
+    int32_t index_base; /* 0 or 1: base of int64 index arrays crossing the host boundary                */
+    int32_t sort_columns; /* != 0: entries of every row sorted by column (CSR form of the CSC the reference builds) */
+    int32_t kernel;     /* 0 = auto, 1 = generic shared-memory LU kernel, 2 = register/DMMA kernel (error if n/a) */
+    int32_t reserved[5];
+} rbffd_options;
+
+typedef struct rbffd_context rbffd_context;     /* one per (device, stream); not thread-safe, thread-compatible */
+typedef struct rbffd_operator rbffd_operator;   /* device-resident operator set sharing one sparsity pattern   */
+
+/* ---- context ------------------------------------------------------------------------------------------ */
+int rbffd_create(int device, rbffd_context** ctx);
+int rbffd_destroy(rbffd_context* ctx);
+const char* rbffd_last_error(const rbffd_context* ctx);    /* valid until the next call on ctx; ctx may be NULL */
+int rbffd_set_stream(rbffd_context* ctx, void* cuda_stream); /* cudaStream_t owned by the caller (e.g. torch)   */
+int rbffd_synchronize(rbffd_context* ctx);
+int rbffd_version(void);
+/* milliseconds (CUDA events) of the phases of the last generate call: [0] binning [1] knn [2] nearest
+ * [3] weights [4] column sort/copies ; n <= 8 */
+int rbffd_timings(rbffd_context* ctx, double* ms, int n);
+
+/* ---- neighbour search --------------------------------------------------------------------------------- */
+/* Replaces KDTree(X); knn(tree, Q, k, true)  (generate_operator.jl:43-47) and, with groups, the masked
+ * search of calculateneighbors (calculateneighbors.jl:16-42,83-87).  group code per node: 0 interior,
+ * 1+2b boundary b, 2+2b ghost set b.  Results ascending by (squared distance, index).
+ * xgroup/qgroup/d2_out may be NULL. */
+int rbffd_knn_device(rbffd_context* ctx, const double* X, int64_t N, int32_t dim,
+                     const double* Q, int64_t NQ, int32_t k,
+                     const int32_t* xgroup, const int32_t* qgroup,
+                     int32_t* idx_out /* NQ*k */, double* d2_out /* NQ*k or NULL */);
+
+/* calculateneighbors(X, Y, n, X_idx_in, X_idx_bc, X_idx_bc_g, ...)  (calculateneighbors.jl:1-97).
+ * xgroup NULL = unmasked (the inline search of generate_operator.jl:43-47).
+ * dist_* receive Euclidean distances (like NearestNeighbors); any output may be NULL. */
+int rbffd_calculateneighbors_host(rbffd_context* ctx, const double* X, int64_t N, const double* Y, int64_t M,
+                                  int32_t dim, int32_t n, const int32_t* xgroup, int32_t index_base,
+                                  int64_t* idxs_x /* N*n */, int64_t* idxs_y_x /* M */,
+                                  double* dists_x /* N*n */, double* dists_y_x /* M */);
+
+/* ---- operator generation ------------------------------------------------------------------------------ */
+/* generate_operator(X, Y, p, n, polydeg[, index sets])  (generate_operator.jl:29, :192) and
+ * hyperviscosity_operator(K, X, Y, p, n, polydeg[, index sets]) (hyperviscosity_operator.jl:26, :177):
+ * one neighbour search and ONE factorisation per X node serve every operator in opts->ops.
+ * Y == NULL means Y = X.  colind_out[M*n] and vals_out[nops*M*n] are caller-allocated host buffers. */
+int rbffd_generate_operator_host(rbffd_context* ctx, const rbffd_options* opts,
+                                 const double* X, int64_t N, const double* Y, int64_t M,
+                                 const int32_t* xgroup, int64_t* colind_out, double* vals_out);
+
+/* same, everything device resident: stencils [N*n] int32 from rbffd_knn_device (or the caller),
+ * center[M] int32 = nearest X node per row.  colind_out int32 [M*n], vals_out [nops*M*n]. */
+int rbffd_weights_device(rbffd_context* ctx, const rbffd_options* opts,
+                         const double* X, int64_t N, const double* Y, int64_t M,
+                         const int32_t* stencils, const int32_t* center,
+                         int32_t* colind_out, double* vals_out);
+
+/* kNN + nearest + weights, device resident; returns an operator handle (matrices never leave HBM). */
+int rbffd_operator_generate(rbffd_context* ctx, const rbffd_options* opts,
+                            const double* X_dev, int64_t N, const double* Y_dev, int64_t M,
+                            const int32_t* xgroup_dev, rbffd_operator** op);
+/* wrap host CSR data (fixed row length) */
+int rbffd_operator_from_host(rbffd_context* ctx, int64_t M, int64_t N, int32_t n, int32_t nmat,
+                             const int64_t* colind, int32_t index_base, const double* vals, rbffd_operator** op);
+int rbffd_operator_destroy(rbffd_operator* op);
+int rbffd_operator_info(const rbffd_operator* op, int64_t* M, int64_t* N, int32_t* n, int32_t* nmat);
+/* device pointers of the shared pattern and of matrix `which` (for callers that manage their own kernels) */
+int rbffd_operator_pointers(const rbffd_operator* op, int32_t which, const int32_t** colind, const double** vals);
+int rbffd_operator_to_host(rbffd_operator* op, int32_t index_base, int64_t* colind_out, double* vals_out);
+
+/* ---- operator application ----------------------------------------------------------------------------- */
+/* y = alpha * D[which] * x + beta * y       (D*u, examples/adv_diff_test.jl:151-152); device pointers */
+int rbffd_spmv_device(rbffd_operator* op, int32_t which, double alpha, const double* x, double beta, double* y);
+/* y = alpha * D[which]' * v + beta * y      (E' * v, adv_diff_test.jl:151); y has N entries */
+int rbffd_spmv_t_device(rbffd_operator* op, int32_t which, double alpha, const double* v, double beta, double* y);
+/* y = sum_i coef[i] * D[which[i]] * x  in ONE pass over the shared pattern (fused multi-operator SpMV) */
+int rbffd_spmv_multi_device(rbffd_operator* op, int32_t nterms, const int32_t* which, const double* coef,
+                            const double* x, double* y);
+int rbffd_spmv_host(rbffd_operator* op, int32_t which, double alpha, const double* x, double beta, double* y);
+int rbffd_spmv_t_host(rbffd_operator* op, int32_t which, double alpha, const double* v, double beta, double* y);
+
+/* du = E' * (alpha*Dxx*u + alpha*Dyy*u - ux*Dx*u - uy*Dy*u) - gamma * (Dxk + Dyk) * u
+ * = the interior line of cons_sys (adv_diff_test.jl:151-152).  iE..iDyk index the operator's matrices;
+ * iDxk/iDyk < 0 drops the hyperviscosity term.  u, du: device, length N (= M). */
+typedef struct {
+    int32_t iE, iDx, iDy, iDxx, iDyy, iDxk, iDyk;
+    int32_t reserved;
+    double alpha, ux, uy, gamma;
+} rbffd_advdiff_params;
+int rbffd_rhs_advdiff_device(rbffd_operator* op, const rbffd_advdiff_params* prm, const double* u, double* du);
+int rbffd_rhs_advdiff_host(rbffd_operator* op, const rbffd_advdiff_params* prm, const double* u, double* du);
+
+/* rows [row0, row1) only, reading x through `xmap` is not needed: sharded operators store LOCAL column
+ * ids into [owned | halo]; pack/unpack kernels move halo values (multi-GPU SpMV). */
+int rbffd_gather_device(rbffd_context* ctx, const double* src, const int32_t* index, int64_t count, double* dst);
+int rbffd_scatter_add_device(rbffd_context* ctx, const double* src, const int32_t* index, int64_t count, double* dst);
+
+/* ---- synthetic node sets: jittered lattice in [0,1]^d, counter-based RNG, on device ------ */
+/* node (i,j[,l]) of a g^d lattice, linear ids [first, first+count): ((i,j,l)+0.5+0.5*(U-0.5))/g */
+int rbffd_jittered_lattice_device(rbffd_context* ctx, int32_t dim, int64_t g, uint64_t seed,
+                                  int64_t first, int64_t count, double* X_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RBFFD_H */

@@ -1,0 +1,450 @@
+// api.cu -- the extern "C" surface of librbffd.so (declared in include/rbffd.h).
+#include <cmath>
+#include <cstring>
+#include <new>
+
+#include "common.cuh"
+
+int rbffd_spmv_multi_impl(rbffd_operator* op, int nterms, const int32_t* which, const double* coef, const double* x,
+                          double beta, double* y);
+int rbffd_spmv_t_impl(rbffd_operator* op, int which, double alpha, const double* v, double beta, double* y);
+int rbffd_gather_impl(rbffd_context* ctx, const double* src, const int32_t* index, int64_t count, double* dst);
+int rbffd_scatter_add_impl(rbffd_context* ctx, const double* src, const int32_t* index, int64_t count, double* dst);
+
+namespace {
+
+thread_local std::string g_err_noctx;
+
+__global__ void i32_to_i64_kernel(const int32_t* __restrict__ in, int64_t n, int64_t base, int64_t* __restrict__ out) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (int64_t)in[i] + base;
+}
+
+__global__ void i64_to_i32_kernel(const int64_t* __restrict__ in, int64_t n, int64_t base, int32_t* __restrict__ out, int64_t hi, int* bad) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) {
+        int64_t v = in[i] - base;
+        if (v < 0 || v >= hi) *bad = 1;
+        out[i] = (int32_t)v;
+    }
+}
+
+__global__ void sqrt_kernel(double* p, int64_t n) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) p[i] = sqrt(p[i]);
+}
+
+__device__ __forceinline__ double lattice_uniform(uint64_t seed, uint64_t lin, int axis) {
+    uint64_t z = seed + 0x9E3779B97F4A7C15ull * (lin * 3ull + (uint64_t)axis + 1ull);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z ^= z >> 31;
+    return (double)(z >> 11) * 0x1.0p-53;
+}
+
+__global__ void lattice_kernel(int dim, int64_t g, uint64_t seed, int64_t first, int64_t count, double* __restrict__ X) {
+    int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= count) return;
+    const int64_t lin = first + t;
+    int64_t c[3] = {lin % g, (lin / g) % g, lin / (g * g)};
+    if (dim == 2) c[1] = lin / g;
+    for (int a = 0; a < dim; ++a) {
+        double u = lattice_uniform(seed, (uint64_t)lin, a);
+        X[t * dim + a] = ((double)c[a] + 0.5 + 0.5 * (u - 0.5)) / (double)g;
+    }
+}
+
+int copy_indices_to_host(rbffd_context* ctx, const int32_t* dev, int64_t count, int64_t base, int64_t* host) {
+    if (!host || count == 0) return RBFFD_OK;
+    DevBuf<int64_t> wide;
+    CUDA_TRY(ctx, wide.alloc(count, ctx->stream));
+    i32_to_i64_kernel<<<ceil_div_i64(count, 256), 256, 0, ctx->stream>>>(dev, count, base, wide.p);
+    CUDA_TRY(ctx, cudaGetLastError());
+    CUDA_TRY(ctx, cudaMemcpyAsync(host, wide.p, sizeof(int64_t) * count, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return RBFFD_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int rbffd_version(void) { return 100; }
+
+int rbffd_create(int device, rbffd_context** out) {
+    if (!out) return RBFFD_ERR_INVALID;
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        g_err_noctx = std::string("no CUDA device available (") + cudaGetErrorString(e) + "); librbffd has no CPU fallback";
+        return RBFFD_ERR_CUDA;
+    }
+    if (device < 0 || device >= count) {
+        g_err_noctx = "device ordinal out of range";
+        return RBFFD_ERR_INVALID;
+    }
+    rbffd_context* ctx = new (std::nothrow) rbffd_context();
+    if (!ctx) return RBFFD_ERR_INVALID;
+    ctx->device = device;
+    e = cudaSetDevice(device);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) {
+        ctx->own_stream = true;
+        for (int i = 0; i < 8 && e == cudaSuccess; ++i) e = cudaEventCreate(&ctx->ev[i]);
+    }
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&ctx->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+    if (e == cudaSuccess) {
+        // keep freed temporaries in the pool: repeated generate calls do not hit the driver allocator
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            uint64_t thresh = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thresh);
+        }
+    }
+    if (e != cudaSuccess) {
+        g_err_noctx = std::string("CUDA error during rbffd_create: ") + cudaGetErrorString(e);
+        delete ctx;
+        return RBFFD_ERR_CUDA;
+    }
+    *out = ctx;
+    return RBFFD_OK;
+}
+
+int rbffd_destroy(rbffd_context* ctx) {
+    if (!ctx) return RBFFD_OK;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (int i = 0; i < 8; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+    if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return RBFFD_OK;
+}
+
+const char* rbffd_last_error(const rbffd_context* ctx) { return ctx ? ctx->err.c_str() : g_err_noctx.c_str(); }
+
+int rbffd_set_stream(rbffd_context* ctx, void* cuda_stream) {
+    if (!ctx) return RBFFD_ERR_INVALID;
+    cudaSetDevice(ctx->device);
+    if (ctx->own_stream && ctx->stream) { cudaStreamSynchronize(ctx->stream); cudaStreamDestroy(ctx->stream); }
+    ctx->stream = (cudaStream_t)cuda_stream;
+    ctx->own_stream = false;
+    return RBFFD_OK;
+}
+
+int rbffd_synchronize(rbffd_context* ctx) {
+    if (!ctx) return RBFFD_ERR_INVALID;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return RBFFD_OK;
+}
+
+int rbffd_timings(rbffd_context* ctx, double* ms, int n) {
+    if (!ctx || !ms) return RBFFD_ERR_INVALID;
+    for (int i = 0; i < n && i < 8; ++i) ms[i] = ctx->timings[i];
+    return RBFFD_OK;
+}
+
+int rbffd_knn_device(rbffd_context* ctx, const double* X, int64_t N, int32_t dim, const double* Q, int64_t NQ, int32_t k,
+                     const int32_t* xgroup, const int32_t* qgroup, int32_t* idx_out, double* d2_out) {
+    if (!ctx) return RBFFD_ERR_INVALID;
+    if (!X || !idx_out) RBFFD_FAIL(ctx, RBFFD_ERR_INVALID, "knn: NULL pointer");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    const bool q_is_x = (Q == nullptr) || (Q == X && NQ == N && qgroup == xgroup);
+    return rbffd_knn_impl(ctx, X, N, dim, Q, NQ, k, xgroup, qgroup, q_is_x, idx_out, d2_out);
+}
+
+int rbffd_calculateneighbors_host(rbffd_context* ctx, const double* X, int64_t N, const double* Y, int64_t M,
+                                  int32_t dim, int32_t n, const int32_t* xgroup, int32_t index_base,
+                                  int64_t* idxs_x, int64_t* idxs_y_x, double* dists_x, double* dists_y_x) {
+    if (!ctx) return RBFFD_ERR_INVALID;
+    if (!X || N < 1) RBFFD_FAIL(ctx, RBFFD_ERR_INVALID, "calculateneighbors: X is empty");
+    if (dim < 1 || dim > 3) RBFFD_FAIL(ctx, RBFFD_ERR_INVALID, "dim must be 1..3");
+    if (index_base != 0 && index_base != 1) RBFFD_FAIL(ctx, RBFFD_ERR_INVALID, "index_base must be 0 or 1");
+    if (!Y) { Y = X; M = N; }
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    DevBuf<double> dX, dY, d2x, d2y;
+    DevBuf<int32_t> dG, dS, dC;
+    CUDA_TRY(ctx, dX.alloc((size_t)N * dim, st));
+    CUDA_TRY(ctx, cudaMemcpyAsync(dX.p, X, sizeof(double) * N * dim, cudaMemcpyHostToDevice, st));
+    const double* dYp = dX.p;
+    if (Y != X) {
+        CUDA_TRY(ctx, dY.alloc((size_t)M * dim, st));
+        CUDA_TRY(ctx, cudaMemcpyAsync(dY.p, Y, sizeof(double) * M * dim, cudaMemcpyHostToDevice, st));
+        dYp = dY.p;
+    }
+    if (xgroup) {
+        CUDA_TRY(ctx, dG.alloc(N, st));
+        CUDA_TRY(ctx, cudaMemcpyAsync(dG.p, xgroup, sizeof(int32_t) * N, cudaMemcpyHostToDevice, st));
+    }
+    const bool want_x = idxs_x || dists_x, want_y = idxs_y_x || dists_y_x;
+    if (want_x) { CUDA_TRY(ctx, dS.alloc((size_t)N * n, st)); if (dists_x) CUDA_TRY(ctx, d2x.alloc((size_t)N * n, st)); }
+    if (want_y) { CUDA_TRY(ctx, dC.alloc(M, st)); if (dists_y_x) CUDA_TRY(ctx, d2y.alloc(M, st)); }
+    RBFFD_TRY(rbffd_stencils_impl(ctx, dX.p, N, dim, dYp, M, n, xgroup ? dG.p : nullptr, want_x ? dS.p : nullptr,
+                                  dists_x ? d2x.p : nullptr, want_y ? dC.p : nullptr, dists_y_x ? d2y.p : nullptr));
+    if (dists_x) {
+        sqrt_kernel<<<ceil_div_i64(N * n, 256), 256, 0, st>>>(d2x.p, N * n);
+        CUDA_TRY(ctx, cudaMemcpyAsync(dists_x, d2x.p, sizeof(double) * N * n, cudaMemcpyDeviceToHost, st));
+    }
+    if (dists_y_x) {
+        sqrt_kernel<<<ceil_div_i64(M, 256), 256, 0, st>>>(d2y.p, M);
+        CUDA_TRY(ctx, cudaMemcpyAsync(dists_y_x, d2y.p, sizeof(double) * M, cudaMemcpyDeviceToHost, st));
+    }
+    if (idxs_x) RBFFD_TRY(copy_indices_to_host(ctx, dS.p, N * n, index_base, idxs_x));
+    if (idxs_y_x) RBFFD_TRY(copy_indices_to_host(ctx, dC.p, M, index_base, idxs_y_x));
+    CUDA_TRY(ctx, cudaStreamSynchronize(st));
+    return RBFFD_OK;
+}
+
+int rbffd_weights_device(rbffd_context* ctx, const rbffd_options* opts, const double* X, int64_t N, const double* Y,
+                         int64_t M, const int32_t* stencils, const int32_t* center, int32_t* colind_out, double* vals_out) {
+    if (!ctx) return RBFFD_ERR_INVALID;
+    if (!X || !stencils || !colind_out || !vals_out) RBFFD_FAIL(ctx, RBFFD_ERR_INVALID, "weights: NULL pointer");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    if (!Y) { Y = X; M = N; }
+    return rbffd_weights_impl(ctx, opts, X, N, Y, M, stencils, center, colind_out, vals_out);
+}
+
+int rbffd_generate_operator_host(rbffd_context* ctx, const rbffd_options* opts, const double* X, int64_t N,
+                                 const double* Y, int64_t M, const int32_t* xgroup, int64_t* colind_out, double* vals_out) {
+    if (!ctx) return RBFFD_ERR_INVALID;
+    RBFFD_TRY(rbffd_validate_options(ctx, opts));
+    if (!X || N < 1) RBFFD_FAIL(ctx, RBFFD_ERR_INVALID, "generate_operator: X is empty");
+    if (!colind_out || !vals_out) RBFFD_FAIL(ctx, RBFFD_ERR_INVALID, "generate_operator: NULL output buffer");
+    if (!Y) { Y = X; M = N; }
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const int dim = opts->dim, n = opts->n;
+    DevBuf<double> dX, dY;
+    DevBuf<int32_t> dG;
+    CUDA_TRY(ctx, dX.alloc((size_t)N * dim, st));
+    CUDA_TRY(ctx, cudaMemcpyAsync(dX.p, X, sizeof(double) * N * dim, cudaMemcpyHostToDevice, st));
+    const double* dYp = dX.p;
+    if (Y != X) {
+        CUDA_TRY(ctx, dY.alloc((size_t)M * dim, st));
+        CUDA_TRY(ctx, cudaMemcpyAsync(dY.p, Y, sizeof(double) * M * dim, cudaMemcpyHostToDevice, st));
+        dYp = dY.p;
+    }
+    if (xgroup) {
+        CUDA_TRY(ctx, dG.alloc(N, st));
+        CUDA_TRY(ctx, cudaMemcpyAsync(dG.p, xgroup, sizeof(int32_t) * N, cudaMemcpyHostToDevice, st));
+    }
+    rbffd_operator* op = nullptr;
+    RBFFD_TRY(rbffd_operator_generate(ctx, opts, dX.p, N, dYp, M, xgroup ? dG.p : nullptr, &op));
+    int rc = rbffd_operator_to_host(op, opts->index_base, colind_out, vals_out);
+    rbffd_operator_destroy(op);
+    return rc;
+}
+
+int rbffd_operator_generate(rbffd_context* ctx, const rbffd_options* opts, const double* X, int64_t N, const double* Y,
+                            int64_t M, const int32_t* xgroup, rbffd_operator** out) {
+    if (!ctx) return RBFFD_ERR_INVALID;
+    if (!out) RBFFD_FAIL(ctx, RBFFD_ERR_INVALID, "operator_generate: NULL output handle");
+    *out = nullptr;
+    RBFFD_TRY(rbffd_validate_options(ctx, opts));
+    if (!X || N < 1) RBFFD_FAIL(ctx, RBFFD_ERR_INVALID, "operator_generate: X is empty");
+    if (!Y) { Y = X; M = N; }
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const int n = opts->n;
+    for (int i = 0; i < 8; ++i) ctx->timings[i] = 0.0;
+    DevBuf<int32_t> stencils, center;
+    CUDA_TRY(ctx, stencils.alloc((size_t)N * n, st));
+    CUDA_TRY(ctx, center.alloc(M, st));
+    RBFFD_TRY(rbffd_stencils_impl(ctx, X, N, opts->dim, Y, M, n, xgroup, stencils.p, nullptr, center.p, nullptr));
+    rbffd_operator* op = new (std::nothrow) rbffd_operator();
+    if (!op) RBFFD_FAIL(ctx, RBFFD_ERR_INVALID, "out of host memory");
+    op->ctx = ctx; op->M = M; op->N = N; op->n = n; op->nmat = opts->nops;
+    cudaError_t e = cudaMalloc((void**)&op->colind, sizeof(int32_t) * (size_t)std::max<int64_t>(M * n, 1));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&op->vals, sizeof(double) * (size_t)std::max<int64_t>(M * n, 1) * opts->nops);
+    if (e != cudaSuccess) { rbffd_operator_destroy(op); RBFFD_FAIL(ctx, RBFFD_ERR_CUDA, "cudaMalloc of the operator failed: %s", cudaGetErrorString(e)); }
+    int rc = rbffd_weights_impl(ctx, opts, X, N, Y, M, stencils.p, center.p, op->colind, op->vals);
+    if (rc != RBFFD_OK) { rbffd_operator_destroy(op); return rc; }
+    *out = op;
+    return RBFFD_OK;
+}
+
+int rbffd_operator_from_host(rbffd_context* ctx, int64_t M, int64_t N, int32_t n, int32_t nmat, const int64_t* colind,
+                             int32_t index_base, const double* vals, rbffd_operator** out) {
+    if (!ctx) return RBFFD_ERR_INVALID;
+    if (!out || !colind || !vals) RBFFD_FAIL(ctx, RBFFD_ERR_INVALID, "operator_from_host: NULL pointer");
+    *out = nullptr;
+    if (M < 0 || N < 1 || n < 1 || nmat < 1) RBFFD_FAIL(ctx, RBFFD_ERR_INVALID, "operator_from_host: bad sizes");
+    if (N > 0x7fffffff) RBFFD_FAIL(ctx, RBFFD_ERR_UNSUPPORTED, "column count exceeds the int32 device index range");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    rbffd_operator* op = new (std::nothrow) rbffd_operator();
+    if (!op) RBFFD_FAIL(ctx, RBFFD_ERR_INVALID, "out of host memory");
+    op->ctx = ctx; op->M = M; op->N = N; op->n = n; op->nmat = nmat;
+    const size_t nnz = (size_t)std::max<int64_t>(M * n, 1);
+    cudaError_t e = cudaMalloc((void**)&op->colind, sizeof(int32_t) * nnz);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&op->vals, sizeof(double) * nnz * nmat);
+    if (e != cudaSuccess) { rbffd_operator_destroy(op); RBFFD_FAIL(ctx, RBFFD_ERR_CUDA, "cudaMalloc of the operator failed: %s", cudaGetErrorString(e)); }
+    DevBuf<int64_t> wide;
+    DevBuf<int> bad;
+    CUDA_TRY(ctx, wide.alloc(nnz, st));
+    CUDA_TRY(ctx, bad.alloc(1, st));
+    CUDA_TRY(ctx, cudaMemsetAsync(bad.p, 0, sizeof(int), st));
+    CUDA_TRY(ctx, cudaMemcpyAsync(wide.p, colind, sizeof(int64_t) * M * n, cudaMemcpyHostToDevice, st));
+    if (M * n > 0) i64_to_i32_kernel<<<ceil_div_i64(M * n, 256), 256, 0, st>>>(wide.p, M * n, index_base, op->colind, N, bad.p);
+    CUDA_TRY(ctx, cudaMemcpyAsync(op->vals, vals, sizeof(double) * M * n * nmat, cudaMemcpyHostToDevice, st));
+    int h_bad = 0;
+    CUDA_TRY(ctx, cudaMemcpyAsync(&h_bad, bad.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(ctx, cudaStreamSynchronize(st));
+    if (h_bad) { rbffd_operator_destroy(op); RBFFD_FAIL(ctx, RBFFD_ERR_INVALID, "operator_from_host: column index out of range"); }
+    *out = op;
+    return RBFFD_OK;
+}
+
+int rbffd_operator_destroy(rbffd_operator* op) {
+    if (!op) return RBFFD_OK;
+    if (op->ctx) { cudaSetDevice(op->ctx->device); cudaStreamSynchronize(op->ctx->stream); }
+    cudaFree(op->colind); cudaFree(op->vals); cudaFree(op->t_ptr); cudaFree(op->t_src); cudaFree(op->work);
+    delete op;
+    return RBFFD_OK;
+}
+
+int rbffd_operator_info(const rbffd_operator* op, int64_t* M, int64_t* N, int32_t* n, int32_t* nmat) {
+    if (!op) return RBFFD_ERR_INVALID;
+    if (M) *M = op->M;
+    if (N) *N = op->N;
+    if (n) *n = op->n;
+    if (nmat) *nmat = op->nmat;
+    return RBFFD_OK;
+}
+
+int rbffd_operator_pointers(const rbffd_operator* op, int32_t which, const int32_t** colind, const double** vals) {
+    if (!op || which < 0 || which >= op->nmat) return RBFFD_ERR_INVALID;
+    if (colind) *colind = op->colind;
+    if (vals) *vals = op->vals + (size_t)op->M * op->n * which;
+    return RBFFD_OK;
+}
+
+int rbffd_operator_to_host(rbffd_operator* op, int32_t index_base, int64_t* colind_out, double* vals_out) {
+    if (!op) return RBFFD_ERR_INVALID;
+    rbffd_context* ctx = op->ctx;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    const int64_t nnz = op->M * op->n;
+    if (vals_out && nnz > 0)
+        CUDA_TRY(ctx, cudaMemcpyAsync(vals_out, op->vals, sizeof(double) * nnz * op->nmat, cudaMemcpyDeviceToHost, ctx->stream));
+    RBFFD_TRY(copy_indices_to_host(ctx, op->colind, nnz, index_base, colind_out));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return RBFFD_OK;
+}
+
+int rbffd_spmv_device(rbffd_operator* op, int32_t which, double alpha, const double* x, double beta, double* y) {
+    if (!op) return RBFFD_ERR_INVALID;
+    CUDA_TRY(op->ctx, cudaSetDevice(op->ctx->device));
+    return rbffd_spmv_multi_impl(op, 1, &which, &alpha, x, beta, y);
+}
+
+int rbffd_spmv_multi_device(rbffd_operator* op, int32_t nterms, const int32_t* which, const double* coef, const double* x, double* y) {
+    if (!op) return RBFFD_ERR_INVALID;
+    CUDA_TRY(op->ctx, cudaSetDevice(op->ctx->device));
+    return rbffd_spmv_multi_impl(op, nterms, which, coef, x, 0.0, y);
+}
+
+int rbffd_spmv_t_device(rbffd_operator* op, int32_t which, double alpha, const double* v, double beta, double* y) {
+    if (!op) return RBFFD_ERR_INVALID;
+    CUDA_TRY(op->ctx, cudaSetDevice(op->ctx->device));
+    return rbffd_spmv_t_impl(op, which, alpha, v, beta, y);
+}
+
+static int host_apply(rbffd_operator* op, int64_t nin, int64_t nout, const double* hin, double beta, double* hout,
+                      int (*fn)(rbffd_operator*, const double*, double*, void*), void* arg) {
+    rbffd_context* ctx = op->ctx;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    DevBuf<double> din, dout;
+    CUDA_TRY(ctx, din.alloc(nin, st));
+    CUDA_TRY(ctx, dout.alloc(nout, st));
+    CUDA_TRY(ctx, cudaMemcpyAsync(din.p, hin, sizeof(double) * nin, cudaMemcpyHostToDevice, st));
+    if (beta != 0.0) CUDA_TRY(ctx, cudaMemcpyAsync(dout.p, hout, sizeof(double) * nout, cudaMemcpyHostToDevice, st));
+    RBFFD_TRY(fn(op, din.p, dout.p, arg));
+    CUDA_TRY(ctx, cudaMemcpyAsync(hout, dout.p, sizeof(double) * nout, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(ctx, cudaStreamSynchronize(st));
+    return RBFFD_OK;
+}
+
+struct SpmvArg { int which; double alpha, beta; };
+
+int rbffd_spmv_host(rbffd_operator* op, int32_t which, double alpha, const double* x, double beta, double* y) {
+    if (!op) return RBFFD_ERR_INVALID;
+    if (!x || !y) RBFFD_FAIL(op->ctx, RBFFD_ERR_INVALID, "spmv: NULL pointer");
+    SpmvArg a{which, alpha, beta};
+    return host_apply(op, op->N, op->M, x, beta, y, [](rbffd_operator* o, const double* in, double* out, void* p) {
+        SpmvArg* s = (SpmvArg*)p;
+        return rbffd_spmv_multi_impl(o, 1, &s->which, &s->alpha, in, s->beta, out);
+    }, &a);
+}
+
+int rbffd_spmv_t_host(rbffd_operator* op, int32_t which, double alpha, const double* v, double beta, double* y) {
+    if (!op) return RBFFD_ERR_INVALID;
+    if (!v || !y) RBFFD_FAIL(op->ctx, RBFFD_ERR_INVALID, "spmv_t: NULL pointer");
+    SpmvArg a{which, alpha, beta};
+    return host_apply(op, op->M, op->N, v, beta, y, [](rbffd_operator* o, const double* in, double* out, void* p) {
+        SpmvArg* s = (SpmvArg*)p;
+        return rbffd_spmv_t_impl(o, s->which, s->alpha, in, s->beta, out);
+    }, &a);
+}
+
+int rbffd_rhs_advdiff_device(rbffd_operator* op, const rbffd_advdiff_params* prm, const double* u, double* du) {
+    if (!op) return RBFFD_ERR_INVALID;
+    rbffd_context* ctx = op->ctx;
+    if (!prm || !u || !du) RBFFD_FAIL(ctx, RBFFD_ERR_INVALID, "rhs_advdiff: NULL pointer");
+    if (op->M != op->N) RBFFD_FAIL(ctx, RBFFD_ERR_INVALID, "rhs_advdiff: the semidiscretisation needs square operators (M == N)");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    if (!op->work) CUDA_TRY(ctx, cudaMalloc((void**)&op->work, sizeof(double) * (size_t)std::max<int64_t>(op->M, 1)));
+    // w = alpha*Dxx*u + alpha*Dyy*u - ux*Dx*u - uy*Dy*u  (zero coefficients are dropped: no traffic for them)
+    int32_t which[4];
+    double coef[4];
+    int nt = 0;
+    if (prm->alpha != 0.0) { which[nt] = prm->iDxx; coef[nt++] = prm->alpha; which[nt] = prm->iDyy; coef[nt++] = prm->alpha; }
+    if (prm->ux != 0.0) { which[nt] = prm->iDx; coef[nt++] = -prm->ux; }
+    if (prm->uy != 0.0) { which[nt] = prm->iDy; coef[nt++] = -prm->uy; }
+    if (nt == 0) CUDA_TRY(ctx, cudaMemsetAsync(op->work, 0, sizeof(double) * op->M, ctx->stream));
+    else RBFFD_TRY(rbffd_spmv_multi_impl(op, nt, which, coef, u, 0.0, op->work));
+    // du = E' * w
+    RBFFD_TRY(rbffd_spmv_t_impl(op, prm->iE, 1.0, op->work, 0.0, du));
+    // du -= gamma * (Dxk + Dyk) * u
+    if (prm->iDxk >= 0 && prm->iDyk >= 0 && prm->gamma != 0.0) {
+        int32_t wk[2] = {prm->iDxk, prm->iDyk};
+        double ck[2] = {-prm->gamma, -prm->gamma};
+        RBFFD_TRY(rbffd_spmv_multi_impl(op, 2, wk, ck, u, 1.0, du));
+    }
+    return RBFFD_OK;
+}
+
+int rbffd_rhs_advdiff_host(rbffd_operator* op, const rbffd_advdiff_params* prm, const double* u, double* du) {
+    if (!op) return RBFFD_ERR_INVALID;
+    if (!prm || !u || !du) RBFFD_FAIL(op->ctx, RBFFD_ERR_INVALID, "rhs_advdiff: NULL pointer");
+    return host_apply(op, op->N, op->N, u, 0.0, du, [](rbffd_operator* o, const double* in, double* out, void* p) {
+        return rbffd_rhs_advdiff_device(o, (const rbffd_advdiff_params*)p, in, out);
+    }, (void*)prm);
+}
+
+int rbffd_gather_device(rbffd_context* ctx, const double* src, const int32_t* index, int64_t count, double* dst) {
+    if (!ctx) return RBFFD_ERR_INVALID;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    return rbffd_gather_impl(ctx, src, index, count, dst);
+}
+
+int rbffd_scatter_add_device(rbffd_context* ctx, const double* src, const int32_t* index, int64_t count, double* dst) {
+    if (!ctx) return RBFFD_ERR_INVALID;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    return rbffd_scatter_add_impl(ctx, src, index, count, dst);
+}
+
+int rbffd_jittered_lattice_device(rbffd_context* ctx, int32_t dim, int64_t g, uint64_t seed, int64_t first, int64_t count, double* X_out) {
+    if (!ctx) return RBFFD_ERR_INVALID;
+    if (dim < 2 || dim > 3 || g < 1 || first < 0 || count < 0 || !X_out) RBFFD_FAIL(ctx, RBFFD_ERR_INVALID, "jittered_lattice: bad arguments");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    if (count == 0) return RBFFD_OK;
+    lattice_kernel<<<ceil_div_i64(count, 256), 256, 0, ctx->stream>>>(dim, g, seed, first, count, X_out);
+    CUDA_TRY(ctx, cudaGetLastError());
+    return RBFFD_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,87 @@
+// common.cuh -- context, error plumbing and small device helpers shared by the librbffd.so kernels.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "../../include/rbffd.h"
+
+struct rbffd_context {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    std::string err;
+    double timings[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    int sm_count = 148;
+    int max_smem_optin = 0;
+};
+
+struct rbffd_operator {
+    rbffd_context* ctx = nullptr;
+    int64_t M = 0, N = 0;
+    int32_t n = 0, nmat = 0;
+    int32_t* colind = nullptr;   // [M*n] device, 0-based, shared by all matrices
+    double* vals = nullptr;      // [nmat][M*n] device
+    // lazily built transpose pattern (for E' * v): CSC of the M x N pattern
+    int32_t* t_ptr = nullptr;    // [N+1]
+    int32_t* t_src = nullptr;    // [M*n] entry id (k*n+j) sorted by column
+    double* work = nullptr;      // [M] scratch
+};
+
+#define RBFFD_FAIL(ctx, code, ...)                                   \
+    do {                                                             \
+        char _b[512];                                                \
+        snprintf(_b, sizeof(_b), __VA_ARGS__);                       \
+        if (ctx) (ctx)->err = _b;                                    \
+        return (code);                                               \
+    } while (0)
+
+#define CUDA_TRY(ctx, expr)                                                                          \
+    do {                                                                                             \
+        cudaError_t _e = (expr);                                                                     \
+        if (_e != cudaSuccess)                                                                       \
+            RBFFD_FAIL(ctx, RBFFD_ERR_CUDA, "CUDA error %s at %s:%d (%s)", cudaGetErrorString(_e),   \
+                       __FILE__, __LINE__, #expr);                                                   \
+    } while (0)
+
+#define RBFFD_TRY(expr)                  \
+    do {                                 \
+        int _rc = (expr);                \
+        if (_rc != RBFFD_OK) return _rc; \
+    } while (0)
+
+// stream-ordered temporary buffer (freed on scope exit, stream ordered)
+template <typename T>
+struct DevBuf {
+    T* p = nullptr;
+    cudaStream_t s = nullptr;
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    cudaError_t alloc(size_t count, cudaStream_t stream) {
+        s = stream;
+        if (count == 0) count = 1;
+        return cudaMallocAsync(reinterpret_cast<void**>(&p), count * sizeof(T), stream);
+    }
+    T* release() { T* q = p; p = nullptr; return q; }
+    ~DevBuf() { if (p) cudaFreeAsync(p, s); }
+};
+
+static inline int ceil_div_i64(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+// ---- internal entry points shared between translation units ----------------------------------------
+struct KnnGridPlan;   // knn.cu
+
+int rbffd_knn_impl(rbffd_context* ctx, const double* X, int64_t N, int dim, const double* Q, int64_t NQ, int k,
+                   const int32_t* xgroup, const int32_t* qgroup, bool q_is_x, int32_t* idx_out, double* d2_out);
+// kNN of X among X (k = n) plus nearest X of every Y row (k = 1) sharing one binning pass.
+int rbffd_stencils_impl(rbffd_context* ctx, const double* X, int64_t N, int dim, const double* Y, int64_t M, int n,
+                        const int32_t* xgroup, int32_t* stencils, double* d2_x, int32_t* center, double* d2_y);
+int rbffd_weights_impl(rbffd_context* ctx, const rbffd_options* opts, const double* X, int64_t N,
+                       const double* Y, int64_t M, const int32_t* stencils, const int32_t* center,
+                       int32_t* colind_out, double* vals_out);
+int rbffd_validate_options(rbffd_context* ctx, const rbffd_options* o);

@@ -1,0 +1,178 @@
+// spmv.cu -- K5/K6 of SURVEY.md §2: application of the fixed-row-length CSR operators.
+//
+// Replaces the SparseMatrixCSC products of the time-stepping RHS (examples/adv_diff_test.jl:151-152):
+//   D*u                      -> spmv_kernel            (coalesced value/index streams, sub-warp team per row)
+//   (a*Dxx + a*Dyy - ...)*u  -> spmv_multi_kernel      (all operators share ONE colind: one gather of u
+//                                                       serves every matrix, no scalar*sparse temporaries)
+//   E' * v                   -> spmv_t_kernel          (deterministic gather over a lazily built CSC view)
+// Bytes per row (algorithmic): 12 n + 16 for one matrix (8n values + 4n int32 indices + x + y).
+#include <cub/device/device_radix_sort.cuh>
+
+#include "common.cuh"
+
+namespace {
+
+// TPR lanes cooperate on one row; a warp covers 32/TPR consecutive rows = one contiguous chunk of HBM.
+template <int TPR, int NMAT>
+__global__ void __launch_bounds__(256) spmv_multi_kernel(int64_t M, int n, const int32_t* __restrict__ colind,
+                                                         const double* __restrict__ v0, const double* __restrict__ v1,
+                                                         const double* __restrict__ v2, const double* __restrict__ v3,
+                                                         double c0, double c1, double c2, double c3,
+                                                         const double* __restrict__ x, double beta, double* __restrict__ y) {
+    const int lane = threadIdx.x & 31;
+    const int t = lane % TPR;
+    const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t row = warp * (32 / TPR) + lane / TPR;
+    double acc = 0.0;
+    if (row < M) {
+        const int64_t base = row * n;
+        for (int j = t; j < n; j += TPR) {
+            const double xv = __ldg(x + __ldg(colind + base + j));
+            double w = c0 * __ldg(v0 + base + j);
+            if (NMAT > 1) w += c1 * __ldg(v1 + base + j);
+            if (NMAT > 2) w += c2 * __ldg(v2 + base + j);
+            if (NMAT > 3) w += c3 * __ldg(v3 + base + j);
+            acc += w * xv;
+        }
+    }
+#pragma unroll
+    for (int o = TPR / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (row < M && t == 0) y[row] = beta == 0.0 ? acc : acc + beta * y[row];
+}
+
+// y[c] = alpha * sum_{entries e in column c} vals[e] * v[e / n] + beta * y[c]   (one warp per column chunk)
+__global__ void spmv_t_kernel(int64_t N, int n, const int32_t* __restrict__ t_ptr, const int32_t* __restrict__ t_src,
+                              const double* __restrict__ vals, const double* __restrict__ v, double alpha, double beta,
+                              double* __restrict__ y) {
+    const int lane = threadIdx.x & 7;
+    const int64_t col = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 3;
+    double acc = 0.0;
+    if (col < N) {
+        const int b = t_ptr[col], e = t_ptr[col + 1];
+        for (int i = b + lane; i < e; i += 8) {
+            const int src = t_src[i];
+            acc += __ldg(vals + src) * __ldg(v + src / n);
+        }
+    }
+    acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    if (col < N && lane == 0) y[col] = beta == 0.0 ? alpha * acc : alpha * acc + beta * y[col];
+}
+
+__global__ void iota_kernel2(int* p, int64_t n) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) p[i] = (int)i;
+}
+
+__global__ void seg_start_kernel2(const int* __restrict__ key_sorted, int64_t n, int nseg, int* __restrict__ start) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i > n) return;
+    int prev = i == 0 ? -1 : key_sorted[i - 1];
+    int cur = i == n ? nseg : key_sorted[i];
+    for (int c = prev + 1; c <= cur; ++c) start[c] = (int)i;
+}
+
+__global__ void gather_kernel(const double* __restrict__ src, const int32_t* __restrict__ index, int64_t count, double* __restrict__ dst) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < count) dst[i] = src[index[i]];
+}
+
+__global__ void scatter_add_kernel(const double* __restrict__ src, const int32_t* __restrict__ index, int64_t count, double* __restrict__ dst) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < count) atomicAdd(dst + index[i], src[i]);
+}
+
+template <int TPR>
+int launch_multi(rbffd_operator* op, int nm, const double* const* v, const double* c, const double* x, double beta, double* y) {
+    rbffd_context* ctx = op->ctx;
+    const int rows_per_block = 256 / TPR;
+    const int grid = ceil_div_i64(op->M, rows_per_block);
+    cudaStream_t st = ctx->stream;
+    switch (nm) {
+        case 1: spmv_multi_kernel<TPR, 1><<<grid, 256, 0, st>>>(op->M, op->n, op->colind, v[0], v[0], v[0], v[0], c[0], 0, 0, 0, x, beta, y); break;
+        case 2: spmv_multi_kernel<TPR, 2><<<grid, 256, 0, st>>>(op->M, op->n, op->colind, v[0], v[1], v[0], v[0], c[0], c[1], 0, 0, x, beta, y); break;
+        case 3: spmv_multi_kernel<TPR, 3><<<grid, 256, 0, st>>>(op->M, op->n, op->colind, v[0], v[1], v[2], v[0], c[0], c[1], c[2], 0, x, beta, y); break;
+        default: spmv_multi_kernel<TPR, 4><<<grid, 256, 0, st>>>(op->M, op->n, op->colind, v[0], v[1], v[2], v[3], c[0], c[1], c[2], c[3], x, beta, y); break;
+    }
+    CUDA_TRY(ctx, cudaGetLastError());
+    return RBFFD_OK;
+}
+
+}  // namespace
+
+// y = sum_i coef[i] * D[which[i]] * x + beta * y ; terms are fused four at a time over the shared pattern
+int rbffd_spmv_multi_impl(rbffd_operator* op, int nterms, const int32_t* which, const double* coef, const double* x,
+                          double beta, double* y) {
+    rbffd_context* ctx = op->ctx;
+    if (nterms < 1) RBFFD_FAIL(ctx, RBFFD_ERR_INVALID, "spmv: need at least one term");
+    for (int i = 0; i < nterms; ++i)
+        if (which[i] < 0 || which[i] >= op->nmat) RBFFD_FAIL(ctx, RBFFD_ERR_INVALID, "spmv: matrix index %d out of range (nmat=%d)", which[i], op->nmat);
+    if (op->M == 0) return RBFFD_OK;
+    const size_t stride = (size_t)op->M * op->n;
+    for (int i0 = 0; i0 < nterms; i0 += 4) {
+        const int nm = std::min(4, nterms - i0);
+        const double* v[4];
+        double c[4];
+        for (int i = 0; i < nm; ++i) { v[i] = op->vals + stride * which[i0 + i]; c[i] = coef[i0 + i]; }
+        const double b = i0 == 0 ? beta : 1.0;
+        int rc;
+        if (op->n <= 12) rc = launch_multi<4>(op, nm, v, c, x, b, y);
+        else if (op->n <= 48) rc = launch_multi<8>(op, nm, v, c, x, b, y);
+        else rc = launch_multi<16>(op, nm, v, c, x, b, y);
+        RBFFD_TRY(rc);
+    }
+    return RBFFD_OK;
+}
+
+int rbffd_build_transpose(rbffd_operator* op) {
+    if (op->t_ptr) return RBFFD_OK;
+    rbffd_context* ctx = op->ctx;
+    cudaStream_t st = ctx->stream;
+    const int64_t nnz = op->M * op->n;
+    if (nnz > 0x7fffffff) RBFFD_FAIL(ctx, RBFFD_ERR_UNSUPPORTED, "transpose view needs nnz < 2^31 per shard");
+    DevBuf<int> ident, keys_sorted, src, ptr;
+    CUDA_TRY(ctx, ident.alloc(nnz, st));
+    CUDA_TRY(ctx, keys_sorted.alloc(nnz, st));
+    CUDA_TRY(ctx, src.alloc(nnz, st));
+    CUDA_TRY(ctx, ptr.alloc(op->N + 1, st));
+    iota_kernel2<<<ceil_div_i64(nnz, 256), 256, 0, st>>>(ident.p, nnz);
+    int bits = 1;
+    while ((1ll << bits) < op->N) ++bits;
+    size_t tmp_bytes = 0;
+    CUDA_TRY(ctx, cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, op->colind, keys_sorted.p, ident.p, src.p, (int)nnz, 0, bits, st));
+    DevBuf<unsigned char> tmp;
+    CUDA_TRY(ctx, tmp.alloc(tmp_bytes, st));
+    CUDA_TRY(ctx, cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, op->colind, keys_sorted.p, ident.p, src.p, (int)nnz, 0, bits, st));
+    seg_start_kernel2<<<ceil_div_i64(nnz + 1, 256), 256, 0, st>>>(keys_sorted.p, nnz, (int)op->N, ptr.p);
+    CUDA_TRY(ctx, cudaGetLastError());
+    CUDA_TRY(ctx, cudaStreamSynchronize(st));
+    op->t_ptr = ptr.release();
+    op->t_src = src.release();
+    return RBFFD_OK;
+}
+
+int rbffd_spmv_t_impl(rbffd_operator* op, int which, double alpha, const double* v, double beta, double* y) {
+    rbffd_context* ctx = op->ctx;
+    if (which < 0 || which >= op->nmat) RBFFD_FAIL(ctx, RBFFD_ERR_INVALID, "spmv_t: matrix index %d out of range", which);
+    RBFFD_TRY(rbffd_build_transpose(op));
+    if (op->N == 0) return RBFFD_OK;
+    const double* vals = op->vals + (size_t)op->M * op->n * which;
+    spmv_t_kernel<<<ceil_div_i64(op->N, 256 / 8), 256, 0, ctx->stream>>>(op->N, op->n, op->t_ptr, op->t_src, vals, v, alpha, beta, y);
+    CUDA_TRY(ctx, cudaGetLastError());
+    return RBFFD_OK;
+}
+
+int rbffd_gather_impl(rbffd_context* ctx, const double* src, const int32_t* index, int64_t count, double* dst) {
+    if (count == 0) return RBFFD_OK;
+    gather_kernel<<<ceil_div_i64(count, 256), 256, 0, ctx->stream>>>(src, index, count, dst);
+    CUDA_TRY(ctx, cudaGetLastError());
+    return RBFFD_OK;
+}
+
+int rbffd_scatter_add_impl(rbffd_context* ctx, const double* src, const int32_t* index, int64_t count, double* dst) {
+    if (count == 0) return RBFFD_OK;
+    scatter_add_kernel<<<ceil_div_i64(count, 256), 256, 0, ctx->stream>>>(src, index, count, dst);
+    CUDA_TRY(ctx, cudaGetLastError());
+    return RBFFD_OK;
+}

@@ -1,0 +1,50 @@
+"""test/poisson_test.jl:19-132 replayed with a pluggable generate_operator (shared by the oracle and GPU tests)."""
+import numpy as np
+import scipy.sparse as sp
+
+
+def csr(colind, vals, ncols):
+    M, n = colind.shape
+    return sp.csr_matrix((vals.ravel(), colind.ravel(), np.arange(0, M * n + 1, n)), shape=(M, ncols))
+
+
+def poisson_error(tominec, gen):
+    """test/poisson_test.jl:19-132 with `gen` standing in for generate_operator (0-based indices)."""
+    X = tominec["X"].copy()
+    Y = tominec["Y"].copy()
+    N, M = len(X), len(Y)
+    iin = tominec["Y_idx_in"] - 1
+    idi = tominec["Y_idx_dirichlet"] - 1
+    ine = tominec["Y_idx_neumann"] - 1
+    xn, yn = tominec["x_normals"][:, 2], tominec["y_normals"][:, 2]
+    # :34-45 overwrite the Y node nearest to each X node by that X node
+    from scipy.spatial import cKDTree
+    nearest = cKDTree(Y).query(X, 1)[1]
+    for i in range(N):
+        Y[nearest[i]] = X[i]
+    p, polydeg = 3, 3
+    n = 2 * 10
+    colind, vals = gen(X, Y, p, n, polydeg)
+    E, Dx, Dy, Dxx, Dyy, Dxy = (csr(colind, v, N) for v in vals)
+    u_exact = lambda x, y: np.sin(2 * np.pi * x * y)
+    f2 = lambda x, y: -4.0 * x**2 * np.pi**2 * np.sin(2 * np.pi * x * y) - 4.0 * y**2 * np.pi**2 * np.sin(2 * np.pi * x * y)
+    f1 = lambda n1, n2, x, y: n2 * x * np.pi * np.cos(2 * np.pi * x * y) * 2.0 + n1 * y * np.pi * np.cos(2 * np.pi * x * y) * 2.0
+    D = np.zeros((M, N))
+    D[iin] = (Dxx + Dyy)[iin].toarray()
+    D[ine] = xn[:, None] * Dx[ine].toarray() + yn[:, None] * Dy[ine].toarray()
+    D[idi] = E[idi].toarray()
+    f = np.zeros(M)
+    f[iin] = f2(Y[iin, 0], Y[iin, 1])
+    f[ine] = f1(xn, yn, Y[ine, 0], Y[ine, 1])
+    f[idi] = u_exact(Y[idi, 0], Y[idi, 1])
+    h = np.mean(cKDTree(X).query(X, 2)[0][:, 1])
+    M0, M1, M2 = len(idi), len(ine), len(iin)
+    D[iin] *= 1 / np.sqrt(M2); f[iin] *= 1 / np.sqrt(M2)
+    D[ine] *= 1 / np.sqrt(M1); f[ine] *= 1 / np.sqrt(M1)
+    D[idi] *= 1 / h / np.sqrt(M0); f[idi] *= 1 / h / np.sqrt(M0)
+    u = np.linalg.lstsq(D, f, rcond=None)[0]
+    uY = E @ u
+    ue = u_exact(Y[:, 0], Y[:, 1])
+    return np.linalg.norm(uY - ue) / np.linalg.norm(ue)
+
+

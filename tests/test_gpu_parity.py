@@ -1,0 +1,248 @@
+"""GPU parity tests (run on the B200 box: pytest -m gpu).  Every call goes through the C ABI of librbffd.so
+(via the ctypes mirror) and is compared with the CPU oracle on the same seeded inputs.
+
+Tolerances (BASELINE.json north_star):
+  * neighbour indices / CSR pattern: bit-exact, ties by (d^2, index)
+  * weights: |w_gpu - w_ref|_inf <= C * eps * cond_1(A_i) * |w_ref|_inf per row, C = 50   (~1e-10 at cond 1e5)
+  * operator application: 1e-12 relative (same weights on both sides)
+"""
+import numpy as np
+import pytest
+
+import rbffd_b200 as rb
+
+pytestmark = pytest.mark.gpu
+EPS = np.finfo(float).eps
+C_TOL = 50.0
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    return rb.Context(0)
+
+
+def _check_weights(vals, ref, cond_rows, names=None):
+    for o in range(ref.shape[0]):
+        err = np.abs(vals[o] - ref[o]).max(axis=1)
+        scale = np.abs(ref[o]).max(axis=1)
+        tol = C_TOL * EPS * cond_rows * scale + 1e-300
+        bad = err > tol
+        assert not bad.any(), (names[o] if names else o, int(bad.sum()), float((err / tol).max()))
+
+
+# ------------------------------------------------------------------------------------------------ kNN
+@pytest.mark.parametrize("d,g,k", [(2, 150, 30), (3, 22, 60), (2, 40, 1), (2, 64, 50)])
+def test_knn_bit_exact_lattice(ctx, oracle, d, g, k):
+    X = rb.nodes.jittered_lattice(d, g, seed=1)
+    idx, idy, dx, dy = rb.calculateneighbors(X, None, k, ctx=ctx)
+    ref, d2 = oracle.knn(X, X, k)
+    assert np.array_equal(idx, ref)
+    assert np.array_equal(dx, np.sqrt(d2))
+    assert np.array_equal(idy[:, 0], np.arange(len(X)))
+    assert np.array_equal(idx[:, 0], np.arange(len(X)))
+
+
+def test_knn_exact_ties_on_regular_lattice(ctx, oracle):
+    g = np.arange(20.0)
+    X = np.stack(np.meshgrid(g, g, indexing="ij"), -1).reshape(-1, 2)
+    X = X[np.random.default_rng(0).permutation(len(X))]
+    idx, _, dx, _ = rb.calculateneighbors(X, None, 13, ctx=ctx)
+    ref, d2 = oracle.knn(X, X, 13, brute=True)
+    assert np.array_equal(idx, ref) and np.array_equal(dx, np.sqrt(d2))
+
+
+def test_knn_tominec_two_sets(ctx, oracle, tominec):
+    X, Y = tominec["X"], tominec["Y"]
+    idx, idy, dx, dy = rb.calculateneighbors(X, Y, 20, ctx=ctx)
+    ref, d2 = oracle.knn(X, X, 20)
+    refy, d2y = oracle.knn(X, Y, 1)
+    assert np.array_equal(idx, ref) and np.array_equal(idy, refy)
+    assert np.array_equal(dy, np.sqrt(d2y))
+
+
+def test_knn_clustered_and_degenerate(ctx, oracle):
+    rng = np.random.default_rng(7)
+    X = np.concatenate([rng.random((3000, 2)) ** 3, 0.5 + 1e-4 * rng.standard_normal((500, 2)), [[5.0, 5.0]]])
+    idx, _, _, _ = rb.calculateneighbors(X, None, 17, ctx=ctx)
+    assert np.array_equal(idx, oracle.knn(X, X, 17)[0])
+    Xl = np.stack([np.linspace(0, 1, 400) ** 2, np.zeros(400)], 1)     # collinear: zero extent along y
+    idx, _, _, _ = rb.calculateneighbors(Xl, None, 5, ctx=ctx)
+    assert np.array_equal(idx, oracle.knn(Xl, Xl, 5)[0])
+    Y = rng.random((300, 2)) * 3 - 1                                    # queries outside the bounding box of X
+    _, idy, _, dy = rb.calculateneighbors(X, Y, 3, ctx=ctx)
+    ry, d2y = oracle.knn(X, Y, 1)
+    assert np.array_equal(idy, ry) and np.array_equal(dy, np.sqrt(d2y))
+
+
+def test_knn_masked_groups(ctx, oracle):
+    rng = np.random.default_rng(3)
+    N = 4000
+    X = rng.random((N, 2))
+    idx_in, bc, gh = range(0, 3000), [range(3000, 3200), range(3200, 3500)], [range(3500, 3700), range(3700, 4000)]
+    idx, idy, _, _ = rb.calculateneighbors(X, X[:100] + 0.001, 25, idx_in, bc, gh, ctx=ctx)
+    ref, cy, _, _ = oracle.calculateneighbors(X, X[:100] + 0.001, 25, (0, 3000), [(3000, 3200), (3200, 3500)],
+                                              [(3500, 3700), (3700, 4000)])
+    assert np.array_equal(idx, ref) and np.array_equal(idy[:, 0], cy)
+
+
+def test_knn_errors(ctx):
+    X = np.random.default_rng(0).random((10, 2))
+    with pytest.raises(rb.RbffdError) as e:
+        rb.calculateneighbors(X, None, 11, ctx=ctx)           # ArgumentError from knn in the reference
+    assert e.value.code == rb._lib.ERR_K_TOO_LARGE
+    with pytest.raises(rb.RbffdError):
+        rb.calculateneighbors(np.array([[0.0, np.nan]] * 5), None, 2, ctx=ctx)
+
+
+# ------------------------------------------------------------------------------------------------ weights
+CASES = [
+    # d, g, p, deg, n, ops
+    (2, 60, 5, 3, 30, ["E", "Dx", "Dy", "Dxx", "Dyy", "Dxy"]),          # config 2 shape, reference operator tuple
+    (2, 40, 5, 3, 30, ["Lap"]),                                         # config 2, Laplacian from one RHS
+    (2, 36, 5, 5, 42, ["E", "Dx", "Dy", "Dxx", "Dyy", "Dxy", ("Dk", 0, 4), ("Dk", 1, 4)]),   # adv_diff_test.jl parameters
+    (2, 36, 5, 4, 50, ["Dxx", "Dyy", ("Dk", 0, 4), ("Dk", 1, 4)]),      # config 3 shape
+    (3, 14, 7, 3, 60, ["Lap", "Dx", "Dy", "Dz"]),                       # config 4 shape
+    (3, 12, 7, 3, 60, ["E", "Dx", "Dy", "Dz", "Dxx", "Dyy", "Dzz", "Dxy", "Dxz", "Dyz"]),
+    (2, 30, 3, 3, 20, ["E", "Dx", "Dy", "Dxx", "Dyy", "Dxy"]),          # poisson_test.jl parameters
+]
+
+
+@pytest.mark.parametrize("d,g,p,deg,n,ops", CASES)
+def test_weights_vs_oracle(ctx, oracle, d, g, p, deg, n, ops):
+    X = rb.nodes.jittered_lattice(d, g, seed=2)
+    colind, vals = rb.generate_raw(X, None, p, n, deg, ops, ctx=ctx)
+    rcol, rvals, cond = oracle.generate_operator(X, X, p, n, deg, ops=ops, mode=0, want_cond=True)
+    assert np.array_equal(colind, rcol)                                 # pattern bit-exact (stencil order)
+    _check_weights(vals, rvals, cond, ops)
+
+
+def test_sorted_pattern_bit_exact(ctx, oracle):
+    X = rb.nodes.jittered_lattice(2, 50, seed=9)
+    colind, vals = rb.generate_raw(X, None, 5, 30, 3, ["Dxx", "Dyy"], ctx=ctx, sort_columns=True)
+    rcol, rvals, cond = oracle.generate_operator(X, X, 5, 30, 3, ops=["Dxx", "Dyy"], want_cond=True)
+    scol, svals = oracle.sort_rows(rcol, list(rvals))
+    assert np.array_equal(colind, scol)
+    _check_weights(vals, np.stack(svals), cond)
+
+
+def test_two_set_oversampled_poisson(ctx, oracle, tominec):
+    """Y != X (generate_operator.jl:89-167): rows share the factorisation of their nearest X node."""
+    from poisson_helper import poisson_error as _poisson_error
+    X, Y = tominec["X"], tominec["Y"]
+    colind, vals = rb.generate_raw(X, Y, 3, 20, 3, ctx=ctx)
+    rcol, rvals, cond = oracle.generate_operator(X, Y, 3, 20, 3, want_cond=True)
+    assert np.array_equal(colind, rcol)
+    center = oracle.knn(X, Y, 1)[0][:, 0]
+    _check_weights(vals, rvals, cond[center], rb.REFERENCE_OPS)
+    # the reference's own assertion (test/poisson_test.jl:132) through the GPU path
+    err = _poisson_error(tominec, lambda X, Y, p, n, deg: rb.generate_raw(X, Y, p, n, deg, ctx=ctx))
+    assert err < float(tominec["poisson_threshold"])
+    assert abs(err - 0.0026579) < 2e-6
+
+
+def test_hyperviscosity_reference_test(ctx, tominec):
+    """test/hyperviscosity_test.jl:13-33 through the mirrored API (isapprox on sparse = Frobenius, rtol sqrt(eps))."""
+    import scipy.sparse.linalg as spl
+    X = tominec["X"]
+    E, Dx, Dy, Dxx, Dyy, Dxy = rb.generate_operator(X, X, 5, 42, 5, ctx=ctx)
+    Dxk, Dyk = rb.hyperviscosity_operator(2, X, X, 5, 42, 5, ctx=ctx)
+    rtol = float(tominec["hyperviscosity_rtol"])
+    for a, b in ((Dxk, Dxx), (Dyk, Dyy)):
+        assert a.shape == b.shape == (2000, 2000)
+        assert spl.norm(a - b) <= rtol * max(spl.norm(a), spl.norm(b))
+        assert spl.norm(a - b) <= 1e-10 * spl.norm(b)
+
+
+def test_boundary_aware_generate(ctx, oracle):
+    rng = np.random.default_rng(5)
+    X = rb.nodes.jittered_lattice(2, 40, seed=4)
+    N = len(X)
+    perm = rng.permutation(N)
+    X = X[perm]
+    sets = (range(0, 1200), [range(1200, 1300), range(1300, 1400)], [range(1400, 1500), range(1500, 1600)])
+    ops = rb.generate_operator(X, X, 3, 20, 3, *sets, None, None, None, ctx=ctx, shape="full")
+    rcol, rvals = oracle.generate_operator(X, X, 3, 20, 3, groups=((0, 1200), [(1200, 1300), (1300, 1400)],
+                                                                   [(1400, 1500), (1500, 1600)]))
+    import scipy.sparse as sp
+    for o in range(6):
+        ref = sp.csr_matrix((rvals[o].ravel(), rcol.ravel(), np.arange(0, N * 20 + 1, 20)), shape=(N, N))
+        diff = abs(ops[o] - ref.tocsc())
+        assert diff.max() <= 1e-7 * abs(ref).max()
+        assert (ops[o] != 0).nnz <= ref.nnz
+
+
+def test_errors(ctx):
+    X = rb.nodes.jittered_lattice(2, 12)
+    with pytest.raises(rb.RbffdError) as e:
+        rb.generate_raw(X, None, 4, 20, 3, ctx=ctx)                      # even PHS power
+    assert e.value.code == rb._lib.ERR_UNSUPPORTED
+    with pytest.raises(rb.RbffdError) as e:
+        rb.generate_raw(X, None, 3, 8, 3, ctx=ctx)                       # n < number of polynomial terms
+    assert e.value.code == rb._lib.ERR_SINGULAR
+    Xd = X.copy()
+    Xd[5] = Xd[6]                                                        # duplicate node -> singular A (SingularException)
+    with pytest.raises(rb.RbffdError) as e:
+        rb.generate_raw(Xd, None, 3, 20, 3, ctx=ctx)
+    assert e.value.code == rb._lib.ERR_SINGULAR
+
+
+# ------------------------------------------------------------------------------------------------ application
+def test_spmv_and_rhs(ctx, oracle):
+    X = rb.nodes.jittered_lattice(2, 70, seed=6)
+    N = len(X)
+    names = ["E", "Dx", "Dy", "Dxx", "Dyy", ("Dk", 0, 4), ("Dk", 1, 4)]
+    colind, vals = rb.generate_raw(X, None, 5, 42, 5, names, ctx=ctx)
+    op = rb.Operator.from_host(ctx, colind, vals, N)
+    rng = np.random.default_rng(0)
+    u = rng.standard_normal(N)
+    for w in range(7):
+        y = op.spmv(w, u)
+        ref = oracle.spmv(colind, vals[w], u)
+        assert np.max(np.abs(y - ref)) <= 1e-12 * np.max(np.abs(ref))
+    y0 = rng.standard_normal(N)
+    y = op.spmv(3, u, alpha=0.5, beta=-2.0, y=y0.copy())
+    ref = oracle.spmv(colind, vals[3], u, 0.5, -2.0, y0.copy())
+    assert np.max(np.abs(y - ref)) <= 1e-12 * np.max(np.abs(ref))
+    yt = op.spmv_t(1, u)
+    reft = oracle.spmv_t(colind, vals[1], u, N)
+    assert np.max(np.abs(yt - reft)) <= 1e-12 * np.max(np.abs(reft))
+    prm = rb.AdvDiffParams(iE=0, iDx=1, iDy=2, iDxx=3, iDyy=4, iDxk=5, iDyk=6, alpha=1.0, ux=0.5, uy=-0.25, gamma=100 * (1 / 70) ** 4)
+    du = op.rhs_advdiff(u, prm)
+    ref = oracle.rhs_advdiff(colind, *vals, 1.0, 0.5, -0.25, prm.gamma, u)
+    assert np.max(np.abs(du - ref)) <= 1e-12 * np.max(np.abs(ref))
+    prm0 = rb.AdvDiffParams(iE=0, iDx=1, iDy=2, iDxx=3, iDyy=4, iDxk=5, iDyk=6, alpha=1.0, ux=0.0, uy=0.0, gamma=prm.gamma)
+    du0 = op.rhs_advdiff(u, prm0)                                       # the shipped example: u_x = u_y = 0 (adv_diff_test.jl:89)
+    ref0 = oracle.rhs_advdiff(colind, *vals, 1.0, 0.0, 0.0, prm.gamma, u)
+    assert np.max(np.abs(du0 - ref0)) <= 1e-12 * np.max(np.abs(ref0))
+    with pytest.raises(ValueError):
+        op.spmv(0, u[:-1])
+
+
+def test_device_resident_pipeline_and_lattice(ctx, oracle):
+    import torch
+    dev = torch.device("cuda:0")
+    g = 300
+    N = g * g
+    Xd = torch.empty((N, 2), dtype=torch.float64, device=dev)
+    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    ctx.jittered_lattice_device(2, g, 0, 0, N, Xd.data_ptr())
+    torch.cuda.synchronize()
+    assert np.array_equal(Xd.cpu().numpy(), rb.nodes.jittered_lattice(2, g, 0))
+    opts = rb.make_options(2, 5, 30, 3, ["Lap"])
+    op = ctx.operator_generate(opts, Xd.data_ptr(), N)
+    x = torch.randn(N, dtype=torch.float64, device=dev)
+    y = torch.empty(N, dtype=torch.float64, device=dev)
+    op.spmv_device(0, x.data_ptr(), y.data_ptr())
+    torch.cuda.synchronize()
+    colind, vals = op.to_host()
+    ref = oracle.spmv(colind, vals[0], x.cpu().numpy())
+    assert np.max(np.abs(y.cpu().numpy() - ref)) <= 1e-12 * np.max(np.abs(ref))
+    # size-independent properties at a size the oracle does not replay in full: Laplacian of a quadratic is exact
+    Xh = Xd.cpu().numpy()
+    f = torch.from_numpy(Xh[:, 0] ** 2 + 3 * Xh[:, 0] * Xh[:, 1] - Xh[:, 1] ** 2 + 2).to(dev)
+    op.spmv_device(0, f.data_ptr(), y.data_ptr())
+    torch.cuda.synchronize()
+    assert float(y.abs().max()) < 1e-6        # Lap = 2 - 2 = 0, cond*eps*|w| ~ 1e5*1e-16*1e6
+    sub = np.random.default_rng(0).choice(N, 2000, replace=False)
+    rcol = oracle.knn(Xh, Xh[sub], 30)[0]
+    assert np.array_equal(colind[sub], rcol)

@@ -1,0 +1,157 @@
+"""Reference-free checks of the CPU oracle (SURVEY.md §9 'independent checks') and of the host-side helpers."""
+import numpy as np
+import pytest
+
+import rbffd_b200 as rb
+
+
+def test_kdtree_equals_bruteforce(oracle):
+    rng = np.random.default_rng(1)
+    for d, N, k in ((2, 3000, 30), (3, 2500, 60), (2, 500, 1)):
+        X = rng.random((N, d))
+        Q = rng.random((400, d))
+        i1, d1 = oracle.knn(X, Q, k)
+        i2, d2 = oracle.knn(X, Q, k, brute=True)
+        assert np.array_equal(i1, i2) and np.array_equal(d1, d2)
+        assert np.all(np.diff(d1, axis=1) >= 0)
+
+
+def test_knn_ties_broken_by_index(oracle):
+    g = np.arange(8.0)
+    X = np.stack(np.meshgrid(g, g, indexing="ij"), -1).reshape(-1, 2)      # exact lattice: many exact distance ties
+    idx, d2 = oracle.knn(X, X, 9)
+    idb, d2b = oracle.knn(X, X, 9, brute=True)
+    assert np.array_equal(idx, idb)
+    for r in range(len(X)):
+        key = list(zip(d2[r], idx[r]))
+        assert key == sorted(key) and idx[r, 0] == r
+
+
+def test_masked_rule_of_calculateneighbors(oracle):
+    """calculateneighbors.jl:16-42: boundary/ghost nodes of boundary b see interior + all boundary + ghosts of b only."""
+    rng = np.random.default_rng(2)
+    N = 600
+    X = rng.random((N, 2))
+    idx_in = (0, 400)
+    bc = [(400, 450), (450, 500)]
+    gh = [(500, 550), (550, 600)]
+    idx, cy, _, _ = oracle.calculateneighbors(X, X, 12, idx_in, bc, gh)
+    kind, bnd = oracle.groups_from_ranges(N, idx_in, bc, gh)
+    for i in range(N):
+        if kind[i] == 0:
+            continue
+        nb = idx[i]
+        ghosts = nb[kind[nb] == 2]
+        assert np.all(bnd[ghosts] == bnd[i])
+    free, _ = oracle.knn(X, X, 12)
+    assert np.array_equal(idx[:400], free[:400])        # interior queries see everything (:83-87)
+    assert np.array_equal(cy, np.arange(N))
+
+
+@pytest.mark.parametrize("p,alpha", [(5, (4, 0)), (7, (6, 0)), (3, (2, 0)), (5, (1, 1)), (7, (0, 2, 1))])
+def test_rbf_derivative_tables_match_sympy(oracle, p, alpha):
+    import sympy as sp
+    d = len(alpha)
+    xs = sp.symbols("x y z")[:d]
+    r = sp.sqrt(sum(v**2 for v in xs))
+    expr = r**p
+    for v, a in zip(xs, alpha):
+        expr = sp.diff(expr, v, a)
+    tab = oracle.rbf_derivative_table(p, d, alpha)
+    rng = np.random.default_rng(0)
+    for _ in range(5):
+        pt = rng.standard_normal(d)
+        rr = np.linalg.norm(pt)
+        mine = sum(c * np.prod(pt ** np.array([e0, e1, e2][:d])) * rr**q for c, e0, e1, e2, q in tab)
+        ref = float(expr.subs(dict(zip(xs, pt))))
+        assert abs(mine - ref) <= 1e-11 * max(1.0, abs(ref))
+
+
+def test_known_closed_forms(oracle):
+    # SURVEY.md §8a probe: p=5,K=4 -> 45 r + 90 x^2/r - 15 x^4/r^3
+    tab = {(int(e0), int(q)): c for c, e0, _, _, q in oracle.rbf_derivative_table(5, 2, (4, 0))}
+    assert tab == {(0, 1): 45.0, (2, -1): 90.0, (4, -3): -15.0}
+
+
+@pytest.mark.parametrize("d,p,deg,n", [(2, 5, 3, 30), (2, 3, 3, 20), (3, 7, 3, 60), (2, 5, 4, 50)])
+def test_polynomial_reproduction_and_row_sums(oracle, d, p, deg, n):
+    g = 24 if d == 2 else 9
+    X = rb.nodes.jittered_lattice(d, g, seed=3)
+    names = ["E", "Dx", "Dy", "Dxx", "Dyy", "Dxy", "Lap"] + (["Dz", "Dzz"] if d == 3 else [])
+    colind, vals, cond = oracle.generate_operator(X, X, p, n, deg, ops=names, want_cond=True)
+    ex = oracle.monomial_exponents(d, deg)[:, :d]
+    tol = 200 * np.finfo(float).eps * cond.max()
+    alphas = {"E": (0, 0, 0), "Dx": (1, 0, 0), "Dy": (0, 1, 0), "Dxx": (2, 0, 0), "Dyy": (0, 2, 0), "Dxy": (1, 1, 0),
+              "Dz": (0, 0, 1), "Dzz": (0, 0, 2)}
+
+    def mono_deriv(e, al, P):
+        out = np.ones(len(P))
+        for a in range(d):
+            if e[a] < al[a]:
+                return np.zeros(len(P))
+            c = np.prod([e[a] - t for t in range(al[a])]) if al[a] else 1.0
+            out = out * c * P[:, a] ** (e[a] - al[a])
+        return out
+
+    for oi, nm in enumerate(names):
+        W = vals[oi]
+        for e in ex:
+            f = np.prod(X ** e, axis=1)
+            got = np.einsum("kj,kj->k", W, f[colind])
+            if nm == "Lap":
+                want = sum(mono_deriv(e, tuple(2 if b == a else 0 for b in range(3)), X) for a in range(d))
+            else:
+                want = mono_deriv(e, alphas[nm], X)
+            scale = np.abs(W).sum(1).max()
+            assert np.max(np.abs(got - want)) <= tol * scale, (nm, e)
+    E = vals[0]
+    assert np.max(np.abs(E.sum(1) - 1)) < 1e-9
+    # Y_k == X_c  =>  E row = unit vector
+    assert np.allclose(E[:, 0], 1.0, atol=1e-7) and np.max(np.abs(E[:, 1:])) < 1e-7
+    # Lap == Dxx + Dyy (+ Dzz) to rounding
+    lap = vals[names.index("Lap")]
+    s2 = vals[names.index("Dxx")] + vals[names.index("Dyy")] + (vals[names.index("Dzz")] if d == 3 else 0)
+    assert np.max(np.abs(lap - s2)) <= tol * np.abs(s2).max()
+
+
+def test_inverse_mode_vs_lu_vs_long_double(oracle):
+    X = rb.nodes.jittered_lattice(2, 20, seed=5)
+    idx, _ = oracle.knn(X, X, 30)
+    ops = oracle.op_table(2, ["Dxx", "Dy"])
+    c = np.arange(len(X))
+    w0, cond = oracle.weights(X, X, idx, c, 5, 30, 3, ops, mode=0, want_cond=True)
+    w1 = oracle.weights(X, X, idx, c, 5, 30, 3, ops, mode=1)
+    w2 = oracle.weights(X, X, idx, c, 5, 30, 3, ops, mode=2)
+    eps = np.finfo(float).eps
+    for w in (w0, w1):
+        err = np.abs(w - w2).max(axis=2) / np.abs(w2).max(axis=2)
+        assert np.all(err <= 50 * eps * cond[None, :])
+
+
+def test_lattice_generator_is_deterministic_and_sliceable():
+    A = rb.nodes.jittered_lattice(3, 7, seed=11)
+    B = rb.nodes.jittered_lattice(3, 7, seed=11, first=100, count=50)
+    assert np.array_equal(A[100:150], B)
+    assert A.min() > 0 and A.max() < 1
+    g = 7
+    cell = np.floor(A * g).astype(int)
+    lin = cell[:, 0] + g * cell[:, 1] + g * g * cell[:, 2]
+    assert np.array_equal(lin, np.arange(g**3))           # one node per lattice cell
+
+
+def test_spmv_and_rhs_oracle_against_scipy(oracle):
+    import scipy.sparse as sp
+    rng = np.random.default_rng(4)
+    M = N = 500
+    n = 9
+    colind = np.stack([rng.choice(N, n, replace=False) for _ in range(M)])
+    mats = rng.standard_normal((7, M, n))
+    u = rng.standard_normal(N)
+    S = [sp.csr_matrix((m.ravel(), colind.ravel(), np.arange(0, M * n + 1, n)), shape=(M, N)) for m in mats]
+    E, Dx, Dy, Dxx, Dyy, Dxk, Dyk = S
+    assert np.allclose(oracle.spmv(colind, mats[1], u, 2.0), 2.0 * (Dx @ u), rtol=1e-13, atol=1e-13)
+    assert np.allclose(oracle.spmv_t(colind, mats[0], u, N), E.T @ u, rtol=1e-13, atol=1e-13)
+    a, ux, uy, gam = 1.0, 0.3, -0.2, 1e-3
+    want = E.T @ (a * (Dxx @ u) + a * (Dyy @ u) - ux * (Dx @ u) - uy * (Dy @ u)) - gam * ((Dxk + Dyk) @ u)
+    got = oracle.rhs_advdiff(colind, *mats, a, ux, uy, gam, u)
+    assert np.allclose(got, want, rtol=1e-12, atol=1e-12)
