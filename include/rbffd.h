@@ -74,6 +74,10 @@ int rbffd_version(void);
 /* milliseconds (CUDA events) of the phases of the last generate call: [0] binning [1] knn [2] nearest
  * [3] weights [4] column sort/copies ; n <= 8 */
 int rbffd_timings(rbffd_context* ctx, double* ms, int n);
+/* number of hand-written kernels launched through ctx so far (CUB sort passes are not counted) */
+long long rbffd_launch_count(const rbffd_context* ctx);
+/* FP64 roofline denominator measured live: dependent-chain DFMA and DMMA (mma.sync.m8n8k4.f64) kernels, TFLOP/s */
+int rbffd_measure_fp64_peak(rbffd_context* ctx, double* dfma_tflops, double* dmma_tflops);
 
 /* ---- neighbour search --------------------------------------------------------------------------------- */
 /* Replaces KDTree(X); knn(tree, Q, k, true)  (generate_operator.jl:43-47) and, with groups, the masked
@@ -102,12 +106,19 @@ int rbffd_generate_operator_host(rbffd_context* ctx, const rbffd_options* opts,
                                  const double* X, int64_t N, const double* Y, int64_t M,
                                  const int32_t* xgroup, int64_t* colind_out, double* vals_out);
 
-/* same, everything device resident: stencils [N*n] int32 from rbffd_knn_device (or the caller),
- * center[M] int32 = nearest X node per row.  colind_out int32 [M*n], vals_out [nops*M*n]. */
+/* same, everything device resident: stencils [NS*n] int32 from rbffd_knn_device (or the caller; entries index
+ * X, entry 0 of a stencil is its centre node; NS <= 0 means NS = N), center[M] int32 = stencil used by row k
+ * (NULL: row k uses stencil k, needs M == NS -- the sharded case: NS owned nodes, N = owned + halo).
+ * colind_out int32 [M*n], vals_out [nops*M*n]. */
 int rbffd_weights_device(rbffd_context* ctx, const rbffd_options* opts,
                          const double* X, int64_t N, const double* Y, int64_t M,
-                         const int32_t* stencils, const int32_t* center,
+                         const int32_t* stencils, int64_t NS, const int32_t* center,
                          int32_t* colind_out, double* vals_out);
+
+/* stencils of every X node (n nearest, masked by xgroup) and the nearest X node of every Y row in one binning
+ * pass -- the two searches of generate_operator.jl:45-47, device resident.  Either output may be NULL. */
+int rbffd_stencils_device(rbffd_context* ctx, const double* X, int64_t N, int32_t dim, const double* Y, int64_t M,
+                          int32_t n, const int32_t* xgroup, int32_t* stencils_out /* N*n */, int32_t* center_out /* M */);
 
 /* kNN + nearest + weights, device resident; returns an operator handle (matrices never leave HBM). */
 int rbffd_operator_generate(rbffd_context* ctx, const rbffd_options* opts,
@@ -116,6 +127,9 @@ int rbffd_operator_generate(rbffd_context* ctx, const rbffd_options* opts,
 /* wrap host CSR data (fixed row length) */
 int rbffd_operator_from_host(rbffd_context* ctx, int64_t M, int64_t N, int32_t n, int32_t nmat,
                              const int64_t* colind, int32_t index_base, const double* vals, rbffd_operator** op);
+/* non-owning view of caller-managed device arrays (colind int32 [M*n] 0-based, vals [nmat][M*n]) */
+int rbffd_operator_from_device(rbffd_context* ctx, int64_t M, int64_t N, int32_t n, int32_t nmat,
+                               const int32_t* colind, const double* vals, rbffd_operator** op);
 int rbffd_operator_destroy(rbffd_operator* op);
 int rbffd_operator_info(const rbffd_operator* op, int64_t* M, int64_t* N, int32_t* n, int32_t* nmat);
 /* device pointers of the shared pattern and of matrix `which` (for callers that manage their own kernels) */

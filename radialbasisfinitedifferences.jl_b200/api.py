@@ -125,9 +125,26 @@ class Context:
     def knn_device(self, X_ptr, N, dim, k, idx_out_ptr, Q_ptr=None, NQ=0, xgroup_ptr=None, qgroup_ptr=None, d2_out_ptr=None):
         self._check(self._L.rbffd_knn_device(self._h, X_ptr, N, dim, Q_ptr, NQ, k, xgroup_ptr, qgroup_ptr, idx_out_ptr, d2_out_ptr))
 
-    def weights_device(self, opts, X_ptr, N, stencils_ptr, colind_ptr, vals_ptr, Y_ptr=None, M=None, center_ptr=None):
+    def weights_device(self, opts, X_ptr, N, stencils_ptr, colind_ptr, vals_ptr, Y_ptr=None, M=None, center_ptr=None, NS=0):
         self._check(self._L.rbffd_weights_device(self._h, C.byref(opts), X_ptr, N, Y_ptr, N if M is None else M,
-                                                 stencils_ptr, center_ptr, colind_ptr, vals_ptr))
+                                                 stencils_ptr, NS, center_ptr, colind_ptr, vals_ptr))
+
+    def stencils_device(self, X_ptr, N, dim, n, stencils_ptr, center_ptr=None, Y_ptr=None, M=None, xgroup_ptr=None):
+        self._check(self._L.rbffd_stencils_device(self._h, X_ptr, N, dim, Y_ptr, N if M is None else M, n, xgroup_ptr,
+                                                  stencils_ptr, center_ptr))
+
+    def operator_from_device(self, M, N, n, nmat, colind_ptr, vals_ptr):
+        h = C.c_void_p()
+        self._check(self._L.rbffd_operator_from_device(self._h, M, N, n, nmat, colind_ptr, vals_ptr, C.byref(h)))
+        return Operator(self, h)
+
+    def launch_count(self) -> int:
+        return int(self._L.rbffd_launch_count(self._h))
+
+    def measure_fp64_peak(self):
+        a, b = C.c_double(), C.c_double()
+        self._check(self._L.rbffd_measure_fp64_peak(self._h, C.byref(a), C.byref(b)))
+        return {"dfma_tflops": a.value, "dmma_tflops": b.value}
 
     def operator_generate(self, opts, X_ptr, N, Y_ptr=None, M=None, xgroup_ptr=None):
         h = C.c_void_p()

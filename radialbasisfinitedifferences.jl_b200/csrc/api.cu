@@ -59,6 +59,7 @@ int copy_indices_to_host(rbffd_context* ctx, const int32_t* dev, int64_t count, 
     DevBuf<int64_t> wide;
     CUDA_TRY(ctx, wide.alloc(count, ctx->stream));
     i32_to_i64_kernel<<<ceil_div_i64(count, 256), 256, 0, ctx->stream>>>(dev, count, base, wide.p);
+    KLAUNCH(ctx);
     CUDA_TRY(ctx, cudaGetLastError());
     CUDA_TRY(ctx, cudaMemcpyAsync(host, wide.p, sizeof(int64_t) * count, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
@@ -140,6 +141,8 @@ int rbffd_synchronize(rbffd_context* ctx) {
     return RBFFD_OK;
 }
 
+long long rbffd_launch_count(const rbffd_context* ctx) { return ctx ? ctx->launches : 0; }
+
 int rbffd_timings(rbffd_context* ctx, double* ms, int n) {
     if (!ctx || !ms) return RBFFD_ERR_INVALID;
     for (int i = 0; i < n && i < 8; ++i) ms[i] = ctx->timings[i];
@@ -198,13 +201,39 @@ int rbffd_calculateneighbors_host(rbffd_context* ctx, const double* X, int64_t N
     return RBFFD_OK;
 }
 
+int rbffd_stencils_device(rbffd_context* ctx, const double* X, int64_t N, int32_t dim, const double* Y, int64_t M,
+                          int32_t n, const int32_t* xgroup, int32_t* stencils_out, int32_t* center_out) {
+    if (!ctx) return RBFFD_ERR_INVALID;
+    if (!X) RBFFD_FAIL(ctx, RBFFD_ERR_INVALID, "stencils: NULL pointer");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    if (!Y) { Y = X; M = N; }
+    return rbffd_stencils_impl(ctx, X, N, dim, Y, M, n, xgroup, stencils_out, nullptr, center_out, nullptr);
+}
+
+int rbffd_operator_from_device(rbffd_context* ctx, int64_t M, int64_t N, int32_t n, int32_t nmat, const int32_t* colind,
+                               const double* vals, rbffd_operator** out) {
+    if (!ctx) return RBFFD_ERR_INVALID;
+    if (!out || !colind || !vals) RBFFD_FAIL(ctx, RBFFD_ERR_INVALID, "operator_from_device: NULL pointer");
+    *out = nullptr;
+    if (M < 0 || N < 1 || n < 1 || nmat < 1) RBFFD_FAIL(ctx, RBFFD_ERR_INVALID, "operator_from_device: bad sizes");
+    rbffd_operator* op = new (std::nothrow) rbffd_operator();
+    if (!op) RBFFD_FAIL(ctx, RBFFD_ERR_INVALID, "out of host memory");
+    op->ctx = ctx; op->M = M; op->N = N; op->n = n; op->nmat = nmat;
+    op->colind = const_cast<int32_t*>(colind);
+    op->vals = const_cast<double*>(vals);
+    op->borrowed = true;
+    *out = op;
+    return RBFFD_OK;
+}
+
 int rbffd_weights_device(rbffd_context* ctx, const rbffd_options* opts, const double* X, int64_t N, const double* Y,
-                         int64_t M, const int32_t* stencils, const int32_t* center, int32_t* colind_out, double* vals_out) {
+                         int64_t M, const int32_t* stencils, int64_t NS, const int32_t* center, int32_t* colind_out, double* vals_out) {
     if (!ctx) return RBFFD_ERR_INVALID;
     if (!X || !stencils || !colind_out || !vals_out) RBFFD_FAIL(ctx, RBFFD_ERR_INVALID, "weights: NULL pointer");
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     if (!Y) { Y = X; M = N; }
-    return rbffd_weights_impl(ctx, opts, X, N, Y, M, stencils, center, colind_out, vals_out);
+    if (NS <= 0) NS = N;
+    return rbffd_weights_impl(ctx, opts, X, N, Y, M, stencils, NS, center, colind_out, vals_out);
 }
 
 int rbffd_generate_operator_host(rbffd_context* ctx, const rbffd_options* opts, const double* X, int64_t N,
@@ -260,7 +289,7 @@ int rbffd_operator_generate(rbffd_context* ctx, const rbffd_options* opts, const
     cudaError_t e = cudaMalloc((void**)&op->colind, sizeof(int32_t) * (size_t)std::max<int64_t>(M * n, 1));
     if (e == cudaSuccess) e = cudaMalloc((void**)&op->vals, sizeof(double) * (size_t)std::max<int64_t>(M * n, 1) * opts->nops);
     if (e != cudaSuccess) { rbffd_operator_destroy(op); RBFFD_FAIL(ctx, RBFFD_ERR_CUDA, "cudaMalloc of the operator failed: %s", cudaGetErrorString(e)); }
-    int rc = rbffd_weights_impl(ctx, opts, X, N, Y, M, stencils.p, center.p, op->colind, op->vals);
+    int rc = rbffd_weights_impl(ctx, opts, X, N, Y, M, stencils.p, N, center.p, op->colind, op->vals);
     if (rc != RBFFD_OK) { rbffd_operator_destroy(op); return rc; }
     *out = op;
     return RBFFD_OK;
@@ -301,7 +330,8 @@ int rbffd_operator_from_host(rbffd_context* ctx, int64_t M, int64_t N, int32_t n
 int rbffd_operator_destroy(rbffd_operator* op) {
     if (!op) return RBFFD_OK;
     if (op->ctx) { cudaSetDevice(op->ctx->device); cudaStreamSynchronize(op->ctx->stream); }
-    cudaFree(op->colind); cudaFree(op->vals); cudaFree(op->t_ptr); cudaFree(op->t_src); cudaFree(op->work);
+    if (!op->borrowed) { cudaFree(op->colind); cudaFree(op->vals); }
+    cudaFree(op->t_ptr); cudaFree(op->t_src); cudaFree(op->work);
     delete op;
     return RBFFD_OK;
 }
@@ -443,6 +473,7 @@ int rbffd_jittered_lattice_device(rbffd_context* ctx, int32_t dim, int64_t g, ui
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     if (count == 0) return RBFFD_OK;
     lattice_kernel<<<ceil_div_i64(count, 256), 256, 0, ctx->stream>>>(dim, g, seed, first, count, X_out);
+    KLAUNCH(ctx);
     CUDA_TRY(ctx, cudaGetLastError());
     return RBFFD_OK;
 }

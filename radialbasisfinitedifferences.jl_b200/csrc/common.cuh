@@ -18,6 +18,7 @@ struct rbffd_context {
     cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     int sm_count = 148;
     int max_smem_optin = 0;
+    long long launches = 0;      // hand-written kernels launched through this context (rbffd_launch_count)
 };
 
 struct rbffd_operator {
@@ -30,6 +31,7 @@ struct rbffd_operator {
     int32_t* t_ptr = nullptr;    // [N+1]
     int32_t* t_src = nullptr;    // [M*n] entry id (k*n+j) sorted by column
     double* work = nullptr;      // [M] scratch
+    bool borrowed = false;       // colind/vals belong to the caller (rbffd_operator_from_device)
 };
 
 #define RBFFD_FAIL(ctx, code, ...)                                   \
@@ -81,7 +83,9 @@ int rbffd_knn_impl(rbffd_context* ctx, const double* X, int64_t N, int dim, cons
 // kNN of X among X (k = n) plus nearest X of every Y row (k = 1) sharing one binning pass.
 int rbffd_stencils_impl(rbffd_context* ctx, const double* X, int64_t N, int dim, const double* Y, int64_t M, int n,
                         const int32_t* xgroup, int32_t* stencils, double* d2_x, int32_t* center, double* d2_y);
-int rbffd_weights_impl(rbffd_context* ctx, const rbffd_options* opts, const double* X, int64_t N,
-                       const double* Y, int64_t M, const int32_t* stencils, const int32_t* center,
+// stencils [NS][n] index into X (NX nodes); row k of the operators uses stencil center[k] (NULL: k, needs M == NS)
+int rbffd_weights_impl(rbffd_context* ctx, const rbffd_options* opts, const double* X, int64_t NX,
+                       const double* Y, int64_t M, const int32_t* stencils, int64_t NS, const int32_t* center,
                        int32_t* colind_out, double* vals_out);
+#define KLAUNCH(ctx) ((ctx)->launches++)
 int rbffd_validate_options(rbffd_context* ctx, const rbffd_options* o);

@@ -342,6 +342,7 @@ int build_bins(rbffd_context* ctx, const double* X, int64_t N, int dim, int k_hi
     CUDA_TRY(ctx, cudaMemcpyAsync(mm.p, init, sizeof(init), cudaMemcpyHostToDevice, st));
     int blocks = (int)std::min<int64_t>((N + 255) / 256, (int64_t)ctx->sm_count * 8);
     bbox_kernel<<<blocks, 256, 0, st>>>(X, N, dim, mm.p, mm.p + 3);
+    KLAUNCH(ctx);
     unsigned long long h_mm[7];
     CUDA_TRY(ctx, cudaMemcpyAsync(h_mm, mm.p, sizeof(h_mm), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(ctx, cudaStreamSynchronize(st));
@@ -401,6 +402,7 @@ int build_bins(rbffd_context* ctx, const double* X, int64_t N, int dim, int k_hi
     if (xgroup) CUDA_TRY(ctx, B.sgroup.alloc(N, st));
     const int nb = ceil_div_i64(N, 256);
     cell_id_kernel<<<nb, 256, 0, st>>>(X, N, dim, g, cid.p, ident.p);
+    KLAUNCH(ctx);
     int bits = 1;
     while ((1ll << bits) < ncells) ++bits;
     size_t tmp_bytes = 0;
@@ -410,6 +412,7 @@ int build_bins(rbffd_context* ctx, const double* X, int64_t N, int dim, int k_hi
     CUDA_TRY(ctx, cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, cid.p, cid_sorted.p, ident.p, B.perm.p, (int)N, 0, bits, st));
     gather_sorted_kernel<<<nb, 256, 0, st>>>(X, N, dim, B.perm.p, xgroup, B.xs.p, xgroup ? B.sgroup.p : nullptr);
     cell_start_kernel<<<ceil_div_i64(N + 1, 256), 256, 0, st>>>(cid_sorted.p, N, (int)ncells, B.cell_start.p);
+    KLAUNCH(ctx); KLAUNCH(ctx);
     CUDA_TRY(ctx, cudaGetLastError());
     return RBFFD_OK;
 }
@@ -443,6 +446,7 @@ int run_knn(rbffd_context* ctx, const Bins& B, const double* Q, int64_t NQ, cons
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         kern<<<nb, KNN_BS, smem, st>>>(a);
+        KLAUNCH(ctx);
         return cudaGetLastError();
     };
     if (B.dim == 1) CUDA_TRY(ctx, launch(knn_kernel<1>));

@@ -95,6 +95,7 @@ int launch_multi(rbffd_operator* op, int nm, const double* const* v, const doubl
         case 3: spmv_multi_kernel<TPR, 3><<<grid, 256, 0, st>>>(op->M, op->n, op->colind, v[0], v[1], v[2], v[0], c[0], c[1], c[2], 0, x, beta, y); break;
         default: spmv_multi_kernel<TPR, 4><<<grid, 256, 0, st>>>(op->M, op->n, op->colind, v[0], v[1], v[2], v[3], c[0], c[1], c[2], c[3], x, beta, y); break;
     }
+    KLAUNCH(ctx);
     CUDA_TRY(ctx, cudaGetLastError());
     return RBFFD_OK;
 }
@@ -159,6 +160,7 @@ int rbffd_spmv_t_impl(rbffd_operator* op, int which, double alpha, const double*
     if (op->N == 0) return RBFFD_OK;
     const double* vals = op->vals + (size_t)op->M * op->n * which;
     spmv_t_kernel<<<ceil_div_i64(op->N, 256 / 8), 256, 0, ctx->stream>>>(op->N, op->n, op->t_ptr, op->t_src, vals, v, alpha, beta, y);
+    KLAUNCH(ctx);
     CUDA_TRY(ctx, cudaGetLastError());
     return RBFFD_OK;
 }
@@ -166,6 +168,7 @@ int rbffd_spmv_t_impl(rbffd_operator* op, int which, double alpha, const double*
 int rbffd_gather_impl(rbffd_context* ctx, const double* src, const int32_t* index, int64_t count, double* dst) {
     if (count == 0) return RBFFD_OK;
     gather_kernel<<<ceil_div_i64(count, 256), 256, 0, ctx->stream>>>(src, index, count, dst);
+    KLAUNCH(ctx);
     CUDA_TRY(ctx, cudaGetLastError());
     return RBFFD_OK;
 }
@@ -173,6 +176,7 @@ int rbffd_gather_impl(rbffd_context* ctx, const double* src, const int32_t* inde
 int rbffd_scatter_add_impl(rbffd_context* ctx, const double* src, const int32_t* index, int64_t count, double* dst) {
     if (count == 0) return RBFFD_OK;
     scatter_add_kernel<<<ceil_div_i64(count, 256), 256, 0, ctx->stream>>>(src, index, count, dst);
+    KLAUNCH(ctx);
     CUDA_TRY(ctx, cudaGetLastError());
     return RBFFD_OK;
 }

@@ -395,8 +395,8 @@ __global__ void sort_rows_kernel(int64_t M, int n, int nops, int32_t* __restrict
 int rbffd_weights_fast(rbffd_context* ctx, const OpTables& T, const double* X, int64_t N, const double* Y, int64_t M,
                        const int32_t* stencils, int32_t* colind_out, double* vals_out, int* fail_flag);
 
-int rbffd_weights_impl(rbffd_context* ctx, const rbffd_options* opts, const double* X, int64_t N,
-                       const double* Y, int64_t M, const int32_t* stencils, const int32_t* center,
+int rbffd_weights_impl(rbffd_context* ctx, const rbffd_options* opts, const double* X, int64_t NX,
+                       const double* Y, int64_t M, const int32_t* stencils, int64_t N, const int32_t* center,
                        int32_t* colind_out, double* vals_out) {
     RBFFD_TRY(rbffd_validate_options(ctx, opts));
     WArgs a;
@@ -404,7 +404,7 @@ int rbffd_weights_impl(rbffd_context* ctx, const rbffd_options* opts, const doub
     build_op_tables(opts, &a.T, msg, sizeof(msg));
     const OpTables& T = a.T;
     if (M == 0) return RBFFD_OK;
-    if (T.n > N) RBFFD_FAIL(ctx, RBFFD_ERR_K_TOO_LARGE, "n=%d exceeds the number of points %lld", T.n, (long long)N);
+    if (T.n > NX) RBFFD_FAIL(ctx, RBFFD_ERR_K_TOO_LARGE, "n=%d exceeds the number of points %lld", T.n, (long long)NX);
     if (T.n > 256) RBFFD_FAIL(ctx, RBFFD_ERR_UNSUPPORTED, "stencil size n=%d > 256", T.n);
     cudaStream_t st = ctx->stream;
     if (!Y) Y = X;
@@ -413,11 +413,13 @@ int rbffd_weights_impl(rbffd_context* ctx, const rbffd_options* opts, const doub
     CUDA_TRY(ctx, flags.alloc(3, st));
     int h_flags[3] = {0x7fffffff, 0, 0};
     CUDA_TRY(ctx, cudaMemcpyAsync(flags.p, h_flags, sizeof(h_flags), cudaMemcpyHostToDevice, st));
-    check_range_kernel<<<ceil_div_i64(N * T.n, 256), 256, 0, st>>>(stencils, N * T.n, (int)N, flags.p + 2);
+    check_range_kernel<<<ceil_div_i64(N * T.n, 256), 256, 0, st>>>(stencils, N * T.n, (int)NX, flags.p + 2);
+    KLAUNCH(ctx);
     bool identity = false;
     if (center) {
         check_range_kernel<<<ceil_div_i64(M, 256), 256, 0, st>>>(center, M, (int)N, flags.p + 2);
-        if (M == N) check_identity_kernel<<<ceil_div_i64(M, 256), 256, 0, st>>>(center, M, flags.p + 1);
+        KLAUNCH(ctx);
+        if (M == N) { check_identity_kernel<<<ceil_div_i64(M, 256), 256, 0, st>>>(center, M, flags.p + 1); KLAUNCH(ctx); }
         CUDA_TRY(ctx, cudaMemcpyAsync(h_flags, flags.p, sizeof(h_flags), cudaMemcpyDeviceToHost, st));
         CUDA_TRY(ctx, cudaStreamSynchronize(st));
         identity = (M == N) && h_flags[1] == 0;
@@ -444,10 +446,12 @@ int rbffd_weights_impl(rbffd_context* ctx, const rbffd_options* opts, const doub
         if (identity) {
             iota_kernel<<<ceil_div_i64(M, 256), 256, 0, st>>>(rows.p, M);
             iota_kernel<<<ceil_div_i64(N + 1, 256), 256, 0, st>>>(seg.p, N + 1);
+            KLAUNCH(ctx); KLAUNCH(ctx);
         } else {
             CUDA_TRY(ctx, keys_sorted.alloc(M, st));
             CUDA_TRY(ctx, ident.alloc(M, st));
             iota_kernel<<<ceil_div_i64(M, 256), 256, 0, st>>>(ident.p, M);
+            KLAUNCH(ctx);
             int bits = 1;
             while ((1ll << bits) < N) ++bits;
             size_t tmp_bytes = 0;
@@ -456,6 +460,7 @@ int rbffd_weights_impl(rbffd_context* ctx, const rbffd_options* opts, const doub
             CUDA_TRY(ctx, tmp.alloc(tmp_bytes, st));
             CUDA_TRY(ctx, cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, center, keys_sorted.p, ident.p, rows.p, (int)M, 0, bits, st));
             seg_start_kernel<<<ceil_div_i64(M + 1, 256), 256, 0, st>>>(keys_sorted.p, M, (int)N, seg.p);
+            KLAUNCH(ctx);
         }
         a.X = X; a.Y = Y; a.stencils = stencils; a.rows = rows.p; a.seg = seg.p;
         a.N = N; a.M = M; a.colind = colind_out; a.vals = vals_out; a.fail = flags.p;
@@ -471,6 +476,7 @@ int rbffd_weights_impl(rbffd_context* ctx, const rbffd_options* opts, const doub
             cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return e;
             kern<<<grid, wpb * 32, smem, st>>>(a, wpb, (int)per_warp);
+            KLAUNCH(ctx);
             return cudaGetLastError();
         };
         if (T.dim == 1) CUDA_TRY(ctx, launch(weights_generic_kernel<1>));
@@ -481,6 +487,7 @@ int rbffd_weights_impl(rbffd_context* ctx, const rbffd_options* opts, const doub
     if (opts->sort_columns) {
         const int wpb = 8;
         sort_rows_kernel<<<ceil_div_i64(M, wpb), wpb * 32, wpb * T.n * sizeof(int), st>>>(M, T.n, T.nops, colind_out, vals_out);
+        KLAUNCH(ctx);
         CUDA_TRY(ctx, cudaGetLastError());
     }
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev[6], st));

@@ -1,0 +1,113 @@
+"""Spatial-block sharding of the hot path across the GPUs of one box.
+
+Every stencil is independent, so nodes are partitioned into contiguous slabs of the synthetic lattice (one slab
+per rank, split along the slowest axis).  Each rank holds  [halo_lo | owned | halo_hi]  node coordinates: the
+halo is generated locally from the closed-form node generator, so WEIGHT GENERATION NEEDS NO COMMUNICATION.
+Column ids of the rank's operator rows are local ids into that layout.  Operator application needs one halo
+exchange of the field per SpMV: the first/last `halo` owned values go to the neighbouring ranks
+(torch.distributed P2P: NCCL send/recv over NVLink on the GPU box, gloo in the CPU tests).
+
+The reference has no distributed code (src/domains/domains.jl:7-8 holds only commented-out includes); this is
+the multi-GPU design of BASELINE.json's north_star.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+
+@dataclass(frozen=True)
+class SlabShard:
+    """Rank `rank` of `world` owns lattice rows [row0, row1) of a g^dim jittered lattice (linear ids x-fastest)."""
+    rank: int
+    world: int
+    dim: int
+    g: int
+    halo_rows: int
+
+    @property
+    def row_size(self) -> int:          # nodes per slowest-axis row (a line in 2-D, a plane in 3-D)
+        return self.g ** (self.dim - 1)
+
+    @property
+    def row0(self) -> int:
+        return (self.g * self.rank) // self.world
+
+    @property
+    def row1(self) -> int:
+        return (self.g * (self.rank + 1)) // self.world
+
+    @property
+    def lo_rows(self) -> int:           # halo rows actually present below / above (domain boundary: none)
+        return min(self.halo_rows, self.row0)
+
+    @property
+    def hi_rows(self) -> int:
+        return min(self.halo_rows, self.g - self.row1)
+
+    @property
+    def n_owned(self) -> int:
+        return (self.row1 - self.row0) * self.row_size
+
+    @property
+    def n_lo(self) -> int:
+        return self.lo_rows * self.row_size
+
+    @property
+    def n_hi(self) -> int:
+        return self.hi_rows * self.row_size
+
+    @property
+    def n_local(self) -> int:
+        return self.n_lo + self.n_owned + self.n_hi
+
+    @property
+    def first_local_id(self) -> int:    # global linear id of local node 0
+        return (self.row0 - self.lo_rows) * self.row_size
+
+    @property
+    def first_owned_id(self) -> int:
+        return self.row0 * self.row_size
+
+    def missing_edges(self):
+        """Slowest-axis coordinates beyond which nodes are NOT present locally: (below, above); None at a domain edge.
+        A lattice row j holds coordinates in [(j+0.25)/g, (j+0.75)/g]."""
+        below = None if self.row0 - self.lo_rows == 0 else (self.row0 - self.lo_rows - 1 + 0.75) / self.g
+        above = None if self.row1 + self.hi_rows == self.g else (self.row1 + self.hi_rows + 0.25) / self.g
+        return below, above
+
+    def halo_is_sufficient(self, x_last_owned, kth_dist2):
+        """Exactness check: every owned stencil's farthest neighbour is strictly closer than any node that is not
+        held locally.  x_last_owned: slowest-axis coordinate of the owned nodes, kth_dist2: their largest squared
+        neighbour distance (torch tensors or NumPy arrays)."""
+        below, above = self.missing_edges()
+        ok = True
+        if below is not None:
+            gap = x_last_owned - below
+            ok = ok and bool(((gap > 0) & (gap * gap > kth_dist2)).all())
+        if above is not None:
+            gap = above - x_last_owned
+            ok = ok and bool(((gap > 0) & (gap * gap > kth_dist2)).all())
+        return ok
+
+
+def exchange_halo(u_local, shard: SlabShard, group=None):
+    """Fill the halo parts of u_local = [halo_lo | owned | halo_hi] (1-D torch tensor) from the neighbouring ranks.
+    The owned part must be current.  One batched send/recv group per call (ncclGroupStart/End under NCCL)."""
+    import torch.distributed as dist
+    s = shard
+    if s.world == 1:
+        return u_local
+    ops = []
+    o0, o1 = s.n_lo, s.n_lo + s.n_owned
+    if s.rank > 0:
+        # rank-1 keeps min(halo_rows, rows it lacks above) rows of ours as its halo_hi: exactly our first rows
+        below = SlabShard(s.rank - 1, s.world, s.dim, s.g, s.halo_rows)
+        ops.append(dist.P2POp(dist.isend, u_local[o0:o0 + below.n_hi], s.rank - 1, group))
+        ops.append(dist.P2POp(dist.irecv, u_local[0:s.n_lo], s.rank - 1, group))
+    if s.rank < s.world - 1:
+        above = SlabShard(s.rank + 1, s.world, s.dim, s.g, s.halo_rows)
+        ops.append(dist.P2POp(dist.isend, u_local[o1 - above.n_lo:o1], s.rank + 1, group))
+        ops.append(dist.P2POp(dist.irecv, u_local[o1:o1 + s.n_hi], s.rank + 1, group))
+    for r in dist.batch_isend_irecv(ops):
+        r.wait()
+    return u_local

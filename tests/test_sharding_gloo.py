@@ -1,0 +1,75 @@
+"""N > 1 host logic on CPU: slab partition invariants and the halo exchange under gloo, world_size 2 and 3."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import rbffd_b200 as rb
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_slab_partition_covers_lattice():
+    for dim, g, world, halo in ((2, 37, 4, 5), (3, 11, 2, 3), (2, 16, 8, 2), (2, 10, 1, 4)):
+        shards = [rb.SlabShard(r, world, dim, g, halo) for r in range(world)]
+        assert sum(s.n_owned for s in shards) == g**dim
+        assert shards[0].n_lo == 0 and shards[-1].n_hi == 0
+        for a, b in zip(shards[:-1], shards[1:]):
+            assert a.row1 == b.row0
+            assert a.first_owned_id + a.n_owned == b.first_owned_id
+        for s in shards:
+            X = rb.nodes.jittered_lattice(dim, g, 0, s.first_local_id, s.n_local)
+            full = rb.nodes.jittered_lattice(dim, g, 0)
+            assert np.array_equal(X, full[s.first_local_id:s.first_local_id + s.n_local])
+            below, above = s.missing_edges()
+            if below is not None:
+                assert full[:s.first_local_id, -1].max() <= below
+            if above is not None:
+                assert full[s.first_local_id + s.n_local:, -1].min() >= above
+
+
+def test_halo_sufficiency_check(oracle):
+    dim, g, world = 2, 40, 2
+    full = rb.nodes.jittered_lattice(dim, g, 0)
+    ref = oracle.knn(full, full, 30)[0]
+    for halo, expect in ((1, False), (8, True)):
+        s = rb.SlabShard(0, world, dim, g, halo)
+        Xl = full[s.first_local_id:s.first_local_id + s.n_local]
+        own = Xl[s.n_lo:s.n_lo + s.n_owned]
+        idx, d2 = oracle.knn(Xl, own, 30)
+        ok = s.halo_is_sufficient(own[:, -1], d2[:, -1])
+        assert ok == expect
+        if ok:      # sufficient halo  =>  local stencils are the global stencils (shifted ids): zero communication
+            assert np.array_equal(idx + s.first_local_id, ref[s.first_owned_id:s.first_owned_id + s.n_owned])
+
+
+def _worker(rank, world, port, dim, g, halo):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sys.path.insert(0, ROOT)
+    import rbffd_b200 as rbw
+    s = rbw.SlabShard(rank, world, dim, g, halo)
+    gid = torch.arange(s.first_local_id, s.first_local_id + s.n_local, dtype=torch.float64)
+    u = torch.full((s.n_local,), -1.0, dtype=torch.float64)
+    u[s.n_lo:s.n_lo + s.n_owned] = gid[s.n_lo:s.n_lo + s.n_owned] * 3.0 + 1.0      # owned values: f(global id)
+    rbw.exchange_halo(u, s)
+    ok = torch.equal(u, gid * 3.0 + 1.0)
+    flag = torch.tensor([1 if ok else 0])
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    dist.destroy_process_group()
+    if flag.item() != 1:
+        raise SystemExit(3)
+
+
+@pytest.mark.parametrize("world,dim,g,halo", [(2, 2, 24, 4), (3, 3, 9, 2)])
+def test_halo_exchange_gloo(world, dim, g, halo):
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
+    mp.spawn(_worker, args=(world, port, dim, g, halo), nprocs=world, join=True)
