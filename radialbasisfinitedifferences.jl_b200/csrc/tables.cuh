@@ -23,11 +23,39 @@ struct OpTables {
     double coef[TAB_MAX_TERMS];
     int8_t te[TAB_MAX_TERMS][4];    // e0,e1,e2, rpow
     int8_t mono[TAB_MAX_MONO][4];   // exponent table, graded order
+    int8_t mpar[TAB_MAX_MONO];      // mono[t] = mono[mpar[t]] * x[maxis[t]]  (t > 0; parents precede children)
+    int8_t maxis[TAB_MAX_MONO];
 };
 
 int build_op_tables(const rbffd_options* o, OpTables* T, char* err, int errlen);
 
 #ifdef __CUDACC__
+// 1/x to ~1 ulp without the IEEE slow path: MUFU.RCP64H seed (about 20 bits) + two Newton steps
+__device__ __forceinline__ double fast_rcp(double x) {
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double e = fma(-x, y, 1.0);
+    y = fma(y, e, y);
+    e = fma(-x, y, 1.0);
+    return fma(y, e, y);
+}
+
+// sqrt(x) for x > 0 (x == 0 -> 0) to ~1 ulp: MUFU.RSQ64H seed + Newton on 1/sqrt + one correction of the root
+__device__ __forceinline__ double fast_sqrt(double x) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double h = 0.5 * y;
+    double e = fma(-x * y, h, 0.5);       // 0.5 - x*y*y/2
+    y = fma(y, e, y);
+    h = 0.5 * y;
+    e = fma(-x * y, h, 0.5);
+    y = fma(y, e, y);
+    double r = x * y;
+    double d = fma(-r, r, x);
+    r = fma(d, 0.5 * y, r);
+    return x > 0.0 ? r : 0.0;
+}
+
 __device__ __forceinline__ double ipow_u(double x, int e) {
     double r = 1.0;
     for (int t = 0; t < e; ++t) r *= x;

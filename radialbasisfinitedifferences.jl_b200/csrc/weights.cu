@@ -83,6 +83,17 @@ int build_op_tables(const rbffd_options* o, OpTables* T, char* err, int errlen) 
                 T->mono[qi][0] = (int8_t)a; T->mono[qi][1] = (int8_t)b; T->mono[qi][2] = (int8_t)c; qi++;
             }
         }
+    for (int tq = 1; tq < qi; ++tq) {
+        int ax = d - 1;
+        while (ax > 0 && T->mono[tq][ax] == 0) --ax;
+        int8_t pe[3] = {T->mono[tq][0], T->mono[tq][1], T->mono[tq][2]};
+        pe[ax] -= 1;
+        int par = 0;
+        for (int u = 0; u < tq; ++u)
+            if (T->mono[u][0] == pe[0] && T->mono[u][1] == pe[1] && T->mono[u][2] == pe[2]) { par = u; break; }
+        T->mpar[tq] = (int8_t)par;
+        T->maxis[tq] = (int8_t)ax;
+    }
     int nt = 0;
     for (int i = 0; i < o->nops; ++i) {
         T->kind[i] = o->ops[i][0];

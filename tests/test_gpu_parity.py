@@ -116,6 +116,36 @@ def test_weights_vs_oracle(ctx, oracle, d, g, p, deg, n, ops):
     _check_weights(vals, rvals, cond, ops)
 
 
+@pytest.mark.parametrize("d,g,p,deg,n,ops", [
+    (2, 50, 5, 3, 30, ["Lap"]), (2, 50, 5, 3, 30, ["E", "Dx", "Dy", "Dxx", "Dyy", "Dxy", ("Dk", 0, 4), ("Dk", 1, 4)]),
+    (2, 40, 3, 3, 20, ["E", "Dx", "Dy"]), (2, 40, 7, 2, 33, ["Lap", "Dxy"]), (2, 40, 5, 4, 31, ["Dxx"]),
+    (3, 12, 5, 2, 36, ["Lap", "Dx", "Dy", "Dz"]), (3, 12, 3, 1, 18, ["Dzz", "Dxz"])])
+def test_dmma_kernel_vs_generic_and_oracle(ctx, oracle, d, g, p, deg, n, ops):
+    """kernel=2 forces the register/DMMA Gauss-Jordan kernel, kernel=1 the shared-memory LU kernel."""
+    X = rb.nodes.jittered_lattice(d, g, seed=8)
+    c2, v2 = rb.generate_raw(X, None, p, n, deg, ops, ctx=ctx, kernel=2)
+    c1, v1 = rb.generate_raw(X, None, p, n, deg, ops, ctx=ctx, kernel=1)
+    rcol, rvals, cond = oracle.generate_operator(X, X, p, n, deg, ops=ops, mode=0, want_cond=True)
+    assert np.array_equal(c2, rcol) and np.array_equal(c1, rcol)
+    _check_weights(v2, rvals, cond, ops)
+    _check_weights(v1, rvals, cond, ops)
+
+
+def test_dmma_kernel_scope(ctx):
+    X = rb.nodes.jittered_lattice(2, 30, seed=1)
+    with pytest.raises(rb.RbffdError) as e:
+        rb.generate_raw(X, None, 5, 42, 5, ["Lap"], ctx=ctx, kernel=2)      # m = 63 > 48: generic kernel only
+    assert e.value.code == rb._lib.ERR_UNSUPPORTED
+    Xd = X.copy()
+    Xd[5] = Xd[6]
+    with pytest.raises(rb.RbffdError) as e:
+        rb.generate_raw(Xd, None, 3, 20, 3, ["Lap"], ctx=ctx, kernel=2)      # duplicate node: rows are no longer collocated
+    assert e.value.code in (rb._lib.ERR_SINGULAR, rb._lib.ERR_UNSUPPORTED)
+    with pytest.raises(rb.RbffdError) as e:
+        rb.generate_raw(Xd, None, 3, 20, 3, ["Lap"], ctx=ctx)
+    assert e.value.code == rb._lib.ERR_SINGULAR
+
+
 def test_sorted_pattern_bit_exact(ctx, oracle):
     X = rb.nodes.jittered_lattice(2, 50, seed=9)
     colind, vals = rb.generate_raw(X, None, 5, 30, 3, ["Dxx", "Dyy"], ctx=ctx, sort_columns=True)
