@@ -45,17 +45,18 @@ def num_monomials(d, deg):
 
 class ClockSampler:
     """nvidia-smi sampling DURING the timed region (profiling recipe, 'clocks line')."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         self.index = index
         self.rows = []
+        self.marks = []
         self.proc = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
                                           "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -65,15 +66,27 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append(line.strip())
 
+    def mark(self):
+        """wall-clock marker: samples taken between two marks belong to the timed region"""
+        self.marks.append(time.time())
+
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.1)
         self.proc.terminate()
+        import datetime
         sm, smax, reasons = [], None, set()
+        lo, hi = (self.marks + [0, 0])[0] - 0.03, (self.marks + [0, 0])[1] + 0.03
         for r in self.rows:
             f = [x.strip() for x in r.split(",")]
             if len(f) < 8:
+                continue
+            try:
+                ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+            except ValueError:
+                continue
+            if len(self.marks) >= 2 and not (lo <= ts <= hi):
                 continue
             try:
                 sm.append(float(f[1]))
@@ -220,6 +233,9 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()           # started before the warm-up so nvidia-smi is already sampling when the timed region begins
     for _ in range(W):
         step(False)
     barrier()
@@ -229,18 +245,17 @@ def main():
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)
         if flag.item() != 1:
             raise SystemExit("halo too narrow for exact stencils: increase halo_rows")
-    clocks = ClockSampler(local_rank)
-    if rank == 0:
-        clocks.start()
     launches0 = ctx.launch_count()
     t_start = torch.cuda.Event(enable_timing=True)
     t_end = torch.cuda.Event(enable_timing=True)
     barrier()
+    clocks.mark()
     t_start.record(stream)
     for _ in range(K):
         step(True)
     t_end.record(stream)
     barrier()
+    clocks.mark()
     elapsed_ms = t_start.elapsed_time(t_end)
     launches = ctx.launch_count() - launches0
     clk = clocks.stop() if rank == 0 else None

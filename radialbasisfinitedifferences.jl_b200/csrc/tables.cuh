@@ -111,6 +111,60 @@ __device__ __forceinline__ double rhs_rbf_entry(const OpTables& T, int o, const 
     return v;
 }
 
+// closed forms for operators of total order <= 2 and the Laplacian (the reference's standard tuple); higher orders
+// (hyperviscosity) go through the term tables.  rp2 = r^(p-2), rp4 = r^(p-4), rp = r^p for this offset.
+template <int D>
+__device__ __forceinline__ double rhs_rbf_entry_fast(const OpTables& T, int o, const double* del, const double* s,
+                                                     double r, double r2, double rp, double rp2, double rp4) {
+    const double pp = (double)T.p, pq = (double)(T.p * (T.p - 2));
+    if (T.kind[o] == RBFFD_OP_LAPLACE) {
+        double v = 0.0;
+#pragma unroll
+        for (int a = 0; a < D; ++a) v += s[a] * s[a] * (pp * rp2 + pq * del[a] * del[a] * rp4);
+        return v;
+    }
+    int order = 0, a0 = -1, a1 = -1;
+#pragma unroll
+    for (int a = 0; a < D; ++a) {
+        const int al = T.alpha[o][a];
+        order += al;
+        if (al >= 1) { if (a0 < 0) a0 = a; else a1 = a; }
+        if (al >= 2) a1 = a;
+    }
+    if (order == 0) return rp;
+    if (order > 2) return eval_rbf_terms<D>(T, T.tb[3 * o], T.tb[3 * o + 1], del, r, r2);
+    double d0 = 0.0, d1 = 0.0;
+#pragma unroll
+    for (int a = 0; a < D; ++a) { if (a == a0) d0 = del[a]; if (a == a1) d1 = del[a]; }
+    if (order == 1) return pp * d0 * rp2;
+    if (a0 == a1) return pp * rp2 + pq * d0 * d0 * rp4;
+    return pq * d0 * d1 * rp4;
+}
+
+// polynomial right-hand-side rows at eta == 0 exactly (collocated rows): d^alpha x^e (0) = alpha! [e == alpha]
+template <int D>
+__device__ __forceinline__ double rhs_poly_entry_at_zero(const OpTables& T, int o, int t, const double* s) {
+    if (T.kind[o] == RBFFD_OP_DERIV) {
+        double v = 1.0;
+#pragma unroll
+        for (int a = 0; a < D; ++a) {
+            const int e = T.mono[t][a], al = T.alpha[o][a];
+            if (e != al) return 0.0;
+            for (int u = 2; u <= al; ++u) v *= (double)u;
+        }
+        return v;
+    }
+    double v = 0.0;
+#pragma unroll
+    for (int a = 0; a < D; ++a) {
+        bool hit = true;
+#pragma unroll
+        for (int b = 0; b < D; ++b) hit = hit && (T.mono[t][b] == (a == b ? 2 : 0));
+        if (hit) v += 2.0 * s[a] * s[a];
+    }
+    return v;
+}
+
 // right-hand-side entry of operator o for monomial t at the scaled evaluation point eta (rows n..m-1)
 template <int D>
 __device__ __forceinline__ double rhs_poly_entry(const OpTables& T, int o, int t, const double* eta, const double* s) {

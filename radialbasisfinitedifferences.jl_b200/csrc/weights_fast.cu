@@ -129,6 +129,7 @@ __global__ void __launch_bounds__(128, (MT <= 5 ? FAST_MIN_BLOCKS : 2)) weights_
         {
             const int half = (n + 1) >> 1;
             const int hp = (T.p - 1) >> 1;
+            const int hp0 = hp;
             for (int tt = 0; tt < half; ++tt) {
                 const int i2 = n - 1 - tt, n1 = n - 1 - tt;
                 for (int cidx = lane; cidx < n - 1; cidx += 32) {
@@ -155,8 +156,11 @@ __global__ void __launch_bounds__(128, (MT <= 5 ? FAST_MIN_BLOCKS : 2)) weights_
                     G[(n + tq) * LDG + j] = v;
                 }
             }
-            for (int qa = 0; qa < q; ++qa)
-                for (int qb = lane; qb < q; qb += 32) G[(n + qa) * LDG + n + qb] = 0.0;
+            {
+                double* zrow = G + n * LDG + n;
+                for (int qa = 0; qa < q; ++qa, zrow += LDG)
+                    for (int qb = lane; qb < q; qb += 32) zrow[qb] = 0.0;
+            }
             if (m < MP) {   // identity padding rows / columns
                 for (int r_ = m; r_ < MP; ++r_)
                     for (int cq = lane; cq < MP; cq += 32) { G[r_ * LDG + cq] = r_ == cq ? 1.0 : 0.0; if (cq < m) G[cq * LDG + r_] = 0.0; }
@@ -165,17 +169,31 @@ __global__ void __launch_bounds__(128, (MT <= 5 ? FAST_MIN_BLOCKS : 2)) weights_
             double eta[D];
 #pragma unroll
             for (int c = 0; c < D; ++c) eta[c] = (a.Y[i * D + c] - xc[c]) * s[c];
+            bool eta_zero = true;
+#pragma unroll
+            for (int c = 0; c < D; ++c) eta_zero = eta_zero && (eta[c] == 0.0);
             for (int j = lane; j < n; j += 32) {
                 double del[D];
+                double r2 = 0.0;
 #pragma unroll
                 for (int c = 0; c < D; ++c) {
                     double dd = eta[c] - S[j * D + c];
                     del[c] = dd == 0.0 ? EPS : dd;
+                    r2 += del[c] * del[c];
                 }
-                for (int o = 0; o < nops; ++o) G[j * LDG + m + o] = rhs_rbf_entry<D>(T, o, del, s);
+                const double r = fast_sqrt(r2);
+                double rp2 = T.p >= 3 ? r : fast_rcp(r);
+                for (int e = 1; e < hp0; ++e) rp2 *= r2;
+                const double rp = rp2 * r2, rp4 = rp2 * fast_rcp(r2);
+                for (int o = 0; o < nops; ++o) G[j * LDG + m + o] = rhs_rbf_entry_fast<D>(T, o, del, s, r, r2, rp, rp2, rp4);
             }
-            for (int tq = lane; tq < q; tq += 32)
-                for (int o = 0; o < nops; ++o) G[(n + tq) * LDG + m + o] = rhs_poly_entry<D>(T, o, tq, eta, s);
+            if (eta_zero) {
+                for (int tq = lane; tq < q; tq += 32)
+                    for (int o = 0; o < nops; ++o) G[(n + tq) * LDG + m + o] = rhs_poly_entry_at_zero<D>(T, o, tq, s);
+            } else {
+                for (int tq = lane; tq < q; tq += 32)
+                    for (int o = 0; o < nops; ++o) G[(n + tq) * LDG + m + o] = rhs_poly_entry<D>(T, o, tq, eta, s);
+            }
         }
         __syncwarp();
         // ---- accumulator fragments: lane (g,t) holds rows 8I+g, columns 8J+2t, 8J+2t+1 ----
@@ -199,10 +217,8 @@ __global__ void __launch_bounds__(128, (MT <= 5 ? FAST_MIN_BLOCKS : 2)) weights_
         // ---- blocked Gauss-Jordan, row-per-lane bookkeeping: lane owns rows lane (slot 0) and lane+32 (slot 1) ----
         constexpr int NZ = MP > 32 ? 2 : 1;
         bool done[NZ];
-        int rpc[NZ];
-        double rri[NZ];
 #pragma unroll
-        for (int z = 0; z < NZ; ++z) { done[z] = (lane + 32 * z) >= MP; rpc[z] = MP; rri[z] = 0.0; }
+        for (int z = 0; z < NZ; ++z) done[z] = (lane + 32 * z) >= MP;
         bool ok = true;
         const bool has1 = lane + 32 < MP;
 
@@ -228,44 +244,47 @@ __global__ void __launch_bounds__(128, (MT <= 5 ? FAST_MIN_BLOCKS : 2)) weights_
                     w[z][cc] = 0.0;
                 }
             // 3. four pivoted Gauss-Jordan steps on the panel
-            int prow[4];
+            unsigned prows = 0;      // 4 pivot rows, 8 bits each (warp-uniform)
 #pragma unroll
             for (int sidx = 0; sidx < 4; ++sidx) {
                 unsigned key = 0;
 #pragma unroll
                 for (int z = 0; z < NZ; ++z) {
-                    unsigned hi = (unsigned)__double2hiint(av[z][sidx]) & 0x7fffffffu;
-                    unsigned kz = done[z] ? 0u : ((hi & 0xffffffc0u) | (unsigned)(z << 5) | (unsigned)lane);
+                    unsigned hi = (unsigned)__double2hiint(av[z][sidx]) & 0x7fffffc0u;
+                    unsigned kz = done[z] ? 0u : (hi | (unsigned)(lane + 32 * z));
                     key = max(key, kz);
                 }
                 const unsigned kmax = __reduce_max_sync(FULL, key);
                 if (kmax < 64u) ok = false;          // zero (or denormal) pivot column: singular
-                const int pl = kmax & 31, pz = (kmax >> 5) & 1;
-                prow[sidx] = pl + 32 * pz;
+                const int pr = kmax & 63;            // pivot row = lane + 32 * slot
+                const int pl = pr & 31;
+                prows |= (unsigned)pr << (8 * sidx);
                 double pv[4], wp[4];
 #pragma unroll
                 for (int cc = sidx; cc < 4; ++cc) {
                     double src = av[0][cc];
-                    if (NZ > 1) src = pz ? av[NZ - 1][cc] : src;
+                    if (NZ > 1) src = (pr & 32) ? av[NZ - 1][cc] : src;
                     pv[cc] = __shfl_sync(FULL, src, pl);
                 }
 #pragma unroll
                 for (int cc = 0; cc < sidx; ++cc) {
                     double src = w[0][cc];
-                    if (NZ > 1) src = pz ? w[NZ - 1][cc] : src;
+                    if (NZ > 1) src = (pr & 32) ? w[NZ - 1][cc] : src;
                     wp[cc] = __shfl_sync(FULL, src, pl);
                 }
                 const double rinv = fast_rcp(pv[sidx]);
+                rinv_s[pr] = rinv;                 // same value from every lane: benign, branch-free
+                pivcol_s[pr] = 4 * kb + sidx;
 #pragma unroll
                 for (int z = 0; z < NZ; ++z) {
-                    const bool ispiv = (lane == pl) && (z == pz);
-                    const double l = ispiv ? 0.0 : av[z][sidx] * rinv;
+                    const bool ispiv = (lane + 32 * z) == pr;
+                    const double nl = ispiv ? 0.0 : av[z][sidx] * (-rinv);
 #pragma unroll
-                    for (int cc = sidx + 1; cc < 4; ++cc) av[z][cc] = fma(-l, pv[cc], av[z][cc]);
+                    for (int cc = sidx + 1; cc < 4; ++cc) av[z][cc] = fma(nl, pv[cc], av[z][cc]);
 #pragma unroll
-                    for (int cc = 0; cc < sidx; ++cc) w[z][cc] = fma(-l, wp[cc], w[z][cc]);
-                    w[z][sidx] = -l;
-                    if (ispiv) { done[z] = true; rpc[z] = 4 * kb + sidx; rri[z] = rinv; }
+                    for (int cc = 0; cc < sidx; ++cc) w[z][cc] = fma(nl, wp[cc], w[z][cc]);
+                    w[z][sidx] = nl;
+                    done[z] = done[z] || ispiv;
                 }
             }
             // 4. transform rows W -> Lbuf -> A fragments
@@ -276,17 +295,24 @@ __global__ void __launch_bounds__(128, (MT <= 5 ? FAST_MIN_BLOCKS : 2)) weights_
                     for (int cc = 0; cc < 4; ++cc) lb_w[cc * PS + 32 * z] = w[z][cc];
                 }
             }
-            // 5. raw pivot rows -> Ubuf: every lane checks whether its row of tile I is one of the 4 pivots
+            // 5. raw pivot rows -> Ubuf: warp-uniform switch on the pivot's tile row, owner lanes (g == row & 7) store
             const int jlo = h == 0 ? Jp : Jp + 1;       // first tile column still alive (tile Jp's right half when h == 0)
 #pragma unroll
-            for (int I = 0; I < MT; ++I) {
-                const int row = 8 * I + g;
-                const int sl = row == prow[0] ? 0 : (row == prow[1] ? 1 : (row == prow[2] ? 2 : (row == prow[3] ? 3 : -1)));
-                if (sl >= 0) {
-                    double2* dst = reinterpret_cast<double2*>(Ubuf + sl * US + 2 * t);
-#pragma unroll
-                    for (int J = 0; J < NT; ++J)
-                        if (J >= jlo) dst[4 * J] = make_double2(c[I][J][0], c[I][J][1]);
+            for (int sidx = 0; sidx < 4; ++sidx) {
+                const int pr = (prows >> (8 * sidx)) & 63;
+                const bool mine = g == (pr & 7);
+                double2* dst = reinterpret_cast<double2*>(Ubuf + sidx * US + 2 * t);
+                switch (pr >> 3) {
+#define RBFFD_DUMP_CASE(II)                                                                           \
+                    case II:                                                                             \
+                        if (II < MT && mine) {                                                           \
+                            _Pragma("unroll") for (int J = 0; J < NT; ++J)                               \
+                                if (J >= jlo) dst[4 * J] = make_double2(c[II < MT ? II : 0][J][0], c[II < MT ? II : 0][J][1]); \
+                        }                                                                                \
+                        break;
+                    RBFFD_DUMP_CASE(0) RBFFD_DUMP_CASE(1) RBFFD_DUMP_CASE(2) RBFFD_DUMP_CASE(3) RBFFD_DUMP_CASE(4) RBFFD_DUMP_CASE(5)
+#undef RBFFD_DUMP_CASE
+                    default: break;
                 }
             }
             __syncwarp();
@@ -306,12 +332,6 @@ __global__ void __launch_bounds__(128, (MT <= 5 ? FAST_MIN_BLOCKS : 2)) weights_
         }
 
         // ---- solution = RHS_row / pivot_row, rescale, scatter into the CSR row ----
-#pragma unroll
-        for (int z = 0; z < NZ; ++z) {
-            const int row = lane + 32 * z;
-            if (row < MP) { rinv_s[row] = rri[z]; pivcol_s[row] = rpc[z]; }
-        }
-        __syncwarp();
         const int64_t krow = i;
         double f[2];
 #pragma unroll
