@@ -13,7 +13,10 @@
 namespace {
 
 // TPR lanes cooperate on one row; a warp covers 32/TPR consecutive rows = one contiguous chunk of HBM.
-template <int TPR, int NMAT>
+// Every lane first issues ALL of its value/index loads (streaming, evict-first), then the gathers of x
+// (read-only path, kept in L1/L2), then the FMAs: ITERS*VEC independent loads in flight per lane.
+// VEC = 2 uses 16-byte value loads and 8-byte index loads (needs an even row length: rows stay 16-byte aligned).
+template <int TPR, int NMAT, int VEC, int ITERS>
 __global__ void __launch_bounds__(256) spmv_multi_kernel(int64_t M, int n, const int32_t* __restrict__ colind,
                                                          const double* __restrict__ v0, const double* __restrict__ v1,
                                                          const double* __restrict__ v2, const double* __restrict__ v3,
@@ -26,14 +29,48 @@ __global__ void __launch_bounds__(256) spmv_multi_kernel(int64_t M, int n, const
     double acc = 0.0;
     if (row < M) {
         const int64_t base = row * n;
-        for (int j = t; j < n; j += TPR) {
-            const double xv = __ldg(x + __ldg(colind + base + j));
-            double w = c0 * __ldg(v0 + base + j);
-            if (NMAT > 1) w += c1 * __ldg(v1 + base + j);
-            if (NMAT > 2) w += c2 * __ldg(v2 + base + j);
-            if (NMAT > 3) w += c3 * __ldg(v3 + base + j);
-            acc += w * xv;
+        int col[ITERS][VEC];
+        double w[ITERS][VEC];
+#pragma unroll
+        for (int it = 0; it < ITERS; ++it) {
+            const int j = (t + it * TPR) * VEC;
+            if (VEC == 2) {
+                if (j < n) {
+                    const int2 ci = __ldcs(reinterpret_cast<const int2*>(colind + base + j));
+                    double2 a0 = __ldcs(reinterpret_cast<const double2*>(v0 + base + j));
+                    a0.x *= c0; a0.y *= c0;
+                    if (NMAT > 1) { const double2 b = __ldcs(reinterpret_cast<const double2*>(v1 + base + j)); a0.x += c1 * b.x; a0.y += c1 * b.y; }
+                    if (NMAT > 2) { const double2 b = __ldcs(reinterpret_cast<const double2*>(v2 + base + j)); a0.x += c2 * b.x; a0.y += c2 * b.y; }
+                    if (NMAT > 3) { const double2 b = __ldcs(reinterpret_cast<const double2*>(v3 + base + j)); a0.x += c3 * b.x; a0.y += c3 * b.y; }
+                    col[it][0] = ci.x; col[it][VEC - 1] = ci.y;
+                    w[it][0] = a0.x; w[it][VEC - 1] = a0.y;
+                } else {
+                    col[it][0] = col[it][VEC - 1] = -1;
+                    w[it][0] = w[it][VEC - 1] = 0.0;
+                }
+            } else {
+                if (j < n) {
+                    col[it][0] = __ldcs(colind + base + j);
+                    double a0 = c0 * __ldcs(v0 + base + j);
+                    if (NMAT > 1) a0 += c1 * __ldcs(v1 + base + j);
+                    if (NMAT > 2) a0 += c2 * __ldcs(v2 + base + j);
+                    if (NMAT > 3) a0 += c3 * __ldcs(v3 + base + j);
+                    w[it][0] = a0;
+                } else {
+                    col[it][0] = -1;
+                    w[it][0] = 0.0;
+                }
+            }
         }
+        double xv[ITERS][VEC];
+#pragma unroll
+        for (int it = 0; it < ITERS; ++it)
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) xv[it][e] = col[it][e] >= 0 ? __ldg(x + col[it][e]) : 0.0;
+#pragma unroll
+        for (int it = 0; it < ITERS; ++it)
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) acc = fma(w[it][e], xv[it][e], acc);
     }
 #pragma unroll
     for (int o = TPR / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
@@ -83,21 +120,46 @@ __global__ void scatter_add_kernel(const double* __restrict__ src, const int32_t
     if (i < count) atomicAdd(dst + index[i], src[i]);
 }
 
-template <int TPR>
+template <int TPR, int VEC, int ITERS>
 int launch_multi(rbffd_operator* op, int nm, const double* const* v, const double* c, const double* x, double beta, double* y) {
     rbffd_context* ctx = op->ctx;
     const int rows_per_block = 256 / TPR;
     const int grid = ceil_div_i64(op->M, rows_per_block);
     cudaStream_t st = ctx->stream;
     switch (nm) {
-        case 1: spmv_multi_kernel<TPR, 1><<<grid, 256, 0, st>>>(op->M, op->n, op->colind, v[0], v[0], v[0], v[0], c[0], 0, 0, 0, x, beta, y); break;
-        case 2: spmv_multi_kernel<TPR, 2><<<grid, 256, 0, st>>>(op->M, op->n, op->colind, v[0], v[1], v[0], v[0], c[0], c[1], 0, 0, x, beta, y); break;
-        case 3: spmv_multi_kernel<TPR, 3><<<grid, 256, 0, st>>>(op->M, op->n, op->colind, v[0], v[1], v[2], v[0], c[0], c[1], c[2], 0, x, beta, y); break;
-        default: spmv_multi_kernel<TPR, 4><<<grid, 256, 0, st>>>(op->M, op->n, op->colind, v[0], v[1], v[2], v[3], c[0], c[1], c[2], c[3], x, beta, y); break;
+        case 1: spmv_multi_kernel<TPR, 1, VEC, ITERS><<<grid, 256, 0, st>>>(op->M, op->n, op->colind, v[0], v[0], v[0], v[0], c[0], 0, 0, 0, x, beta, y); break;
+        case 2: spmv_multi_kernel<TPR, 2, VEC, ITERS><<<grid, 256, 0, st>>>(op->M, op->n, op->colind, v[0], v[1], v[0], v[0], c[0], c[1], 0, 0, x, beta, y); break;
+        case 3: spmv_multi_kernel<TPR, 3, VEC, ITERS><<<grid, 256, 0, st>>>(op->M, op->n, op->colind, v[0], v[1], v[2], v[0], c[0], c[1], c[2], 0, x, beta, y); break;
+        default: spmv_multi_kernel<TPR, 4, VEC, ITERS><<<grid, 256, 0, st>>>(op->M, op->n, op->colind, v[0], v[1], v[2], v[3], c[0], c[1], c[2], c[3], x, beta, y); break;
     }
     KLAUNCH(ctx);
     CUDA_TRY(ctx, cudaGetLastError());
     return RBFFD_OK;
+}
+
+// row length -> (team size, vector width, unrolled iterations); TPR*VEC*ITERS >= n
+int dispatch_multi(rbffd_operator* op, int nm, const double* const* v, const double* c, const double* x, double beta, double* y) {
+    const int n = op->n;
+    bool even = (n % 2) == 0;            // rows start 16-byte aligned when the planes are (n*8 bytes per row)
+    for (int i = 0; i < nm; ++i) even = even && (reinterpret_cast<uintptr_t>(v[i]) % 16 == 0);
+    even = even && (reinterpret_cast<uintptr_t>(op->colind) % 8 == 0);
+    if (even) {
+        if (n <= 8) return launch_multi<4, 2, 1>(op, nm, v, c, x, beta, y);
+        if (n <= 16) return launch_multi<4, 2, 2>(op, nm, v, c, x, beta, y);
+        if (n <= 32) return launch_multi<8, 2, 2>(op, nm, v, c, x, beta, y);
+        if (n <= 48) return launch_multi<8, 2, 3>(op, nm, v, c, x, beta, y);
+        if (n <= 64) return launch_multi<8, 2, 4>(op, nm, v, c, x, beta, y);
+        if (n <= 128) return launch_multi<16, 2, 4>(op, nm, v, c, x, beta, y);
+        if (n <= 256) return launch_multi<32, 2, 4>(op, nm, v, c, x, beta, y);
+    } else {
+        if (n <= 8) return launch_multi<4, 1, 2>(op, nm, v, c, x, beta, y);
+        if (n <= 16) return launch_multi<4, 1, 4>(op, nm, v, c, x, beta, y);
+        if (n <= 32) return launch_multi<8, 1, 4>(op, nm, v, c, x, beta, y);
+        if (n <= 64) return launch_multi<8, 1, 8>(op, nm, v, c, x, beta, y);
+        if (n <= 128) return launch_multi<16, 1, 8>(op, nm, v, c, x, beta, y);
+        if (n <= 256) return launch_multi<32, 1, 8>(op, nm, v, c, x, beta, y);
+    }
+    RBFFD_FAIL(op->ctx, RBFFD_ERR_UNSUPPORTED, "spmv: row length %d > 256", n);
 }
 
 }  // namespace
@@ -117,10 +179,7 @@ int rbffd_spmv_multi_impl(rbffd_operator* op, int nterms, const int32_t* which, 
         double c[4];
         for (int i = 0; i < nm; ++i) { v[i] = op->vals + stride * which[i0 + i]; c[i] = coef[i0 + i]; }
         const double b = i0 == 0 ? beta : 1.0;
-        int rc;
-        if (op->n <= 12) rc = launch_multi<4>(op, nm, v, c, x, b, y);
-        else if (op->n <= 48) rc = launch_multi<8>(op, nm, v, c, x, b, y);
-        else rc = launch_multi<16>(op, nm, v, c, x, b, y);
+        int rc = dispatch_multi(op, nm, v, c, x, b, y);
         RBFFD_TRY(rc);
     }
     return RBFFD_OK;
