@@ -25,7 +25,13 @@ sys.path.insert(0, ROOT)
 
 METRIC = "rbffd_stencils_per_s"
 UNIT = "stencils/s"
-CFG = {"dim": 2, "p": 5, "polydeg": 3, "n": 30, "ops": ["Lap"], "g": 1000}      # configs[1]
+CFG = {"dim": 2, "p": 5, "polydeg": 3, "n": 30, "ops": ["Lap"], "g": 1000}      # configs[1] (the headline workload)
+# supplementary workloads (python bench.py --config N): the other BASELINE.json configs at single-GPU sizes
+CONFIGS = {
+    2: CFG,
+    3: {"dim": 2, "p": 5, "polydeg": 4, "n": 50, "ops": ["Dxx", "Dyy", ("Dk", 0, 4), ("Dk", 1, 4)], "g": 1000},   # configs[2] shape
+    4: {"dim": 3, "p": 7, "polydeg": 3, "n": 60, "ops": ["Lap", "Dx", "Dy", "Dz"], "g": 100},                     # configs[3] shape
+}
 
 
 def flops_per_stencil(m, r):
@@ -157,8 +163,13 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--kernel", type=int, default=0)
+    ap.add_argument("--config", type=int, default=2, choices=[2, 3, 4], help="BASELINE.json config shape (2 = headline)")
     ap.add_argument("--profile", action="store_true", help="ncu passes: honour small --warmup, skip e2e and the CPU baseline")
     args = ap.parse_args()
+    if args.config != 2:
+        CFG.update(CONFIGS[args.config])
+        if args.g == 1000:
+            args.g = CFG["g"]
     if args.impl == "reference":
         return run_reference(args)
 
@@ -321,8 +332,10 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "configs[1]: 2D Laplacian operator, %d jittered-lattice nodes per GPU, PHS r^5 + deg-3 polynomials, "
-                                   "k=30 (m=%d, r=%d)" % (M, m, r),
+            "config": {"workload": ("configs[1]: 2D Laplacian operator, %d jittered-lattice nodes per GPU, PHS r^5 + deg-3 polynomials, "
+                                    "k=30 (m=%d, r=%d)" % (M, m, r)) if args.config == 2 else
+                                   ("configs[%d] shape: %dD, %d nodes per GPU, p=%d, polydeg=%d, k=%d (m=%d, r=%d) ops=%s"
+                                    % (args.config - 1, dim, M, p, deg, n, m, r, CFG["ops"])),
                        "step": "exact kNN + fused weight solve -> CSR + one SpMV (halo exchange first if N>1); nodes resident in HBM",
                        "l2": "every step writes %.0f MB of stencils+operator (> 126 MB L2), so no input survives in L2 between steps" % ((M * n * 4 * 2 + r * M * n * 8) / 1e6),
                        "parallelism": "slab x%d, halo_rows=%d" % (world, halo_rows), "global_nodes": total_nodes},

@@ -56,7 +56,7 @@ struct FastCfg {
     static constexpr int MP = 8 * MT;            // padded system size
     static constexpr int NT = MT + 1;            // tile columns incl. the RHS tile
     static constexpr int NC = 8 * NT;
-    static constexpr int LDG = (MP + 8) | 1;     // staging row stride (odd): columns [0,m) matrix, [m,m+nops) RHS
+    static constexpr int LDG = (MP + 8) | 1;     // staging row stride (odd): columns [0,MP) matrix (identity padded), [MP,MP+nops) RHS
     static constexpr int PS = pad4mod16(MP);     // panel / multiplier buffer stride
     static constexpr int US = pad4mod16(NC);     // pivot-row buffer stride
     static constexpr int NSMAX = 48;             // max stencil size n
@@ -185,14 +185,14 @@ __global__ void __launch_bounds__(128, (MT <= 5 ? FAST_MIN_BLOCKS : 2)) weights_
                 double rp2 = T.p >= 3 ? r : fast_rcp(r);
                 for (int e = 1; e < hp0; ++e) rp2 *= r2;
                 const double rp = rp2 * r2, rp4 = rp2 * fast_rcp(r2);
-                for (int o = 0; o < nops; ++o) G[j * LDG + m + o] = rhs_rbf_entry_fast<D>(T, o, del, s, r, r2, rp, rp2, rp4);
+                for (int o = 0; o < nops; ++o) G[j * LDG + MP + o] = rhs_rbf_entry_fast<D>(T, o, del, s, r, r2, rp, rp2, rp4);
             }
             if (eta_zero) {
                 for (int tq = lane; tq < q; tq += 32)
-                    for (int o = 0; o < nops; ++o) G[(n + tq) * LDG + m + o] = rhs_poly_entry_at_zero<D>(T, o, tq, s);
+                    for (int o = 0; o < nops; ++o) G[(n + tq) * LDG + MP + o] = rhs_poly_entry_at_zero<D>(T, o, tq, s);
             } else {
                 for (int tq = lane; tq < q; tq += 32)
-                    for (int o = 0; o < nops; ++o) G[(n + tq) * LDG + m + o] = rhs_poly_entry<D>(T, o, tq, eta, s);
+                    for (int o = 0; o < nops; ++o) G[(n + tq) * LDG + MP + o] = rhs_poly_entry<D>(T, o, tq, eta, s);
             }
         }
         __syncwarp();
@@ -207,7 +207,7 @@ __global__ void __launch_bounds__(128, (MT <= 5 ? FAST_MIN_BLOCKS : 2)) weights_
                     c[I][J][0] = gl[8 * I * LDG + 8 * J];
                     c[I][J][1] = gl[8 * I * LDG + 8 * J + 1];
                 }
-                const double r0 = gl[8 * I * LDG + m], r1 = gl[8 * I * LDG + m + 1];
+                const double r0 = gl[8 * I * LDG + MP], r1 = gl[8 * I * LDG + MP + 1];
                 c[I][MT][0] = (8 * I + g < m && 2 * t < nops) ? r0 : 0.0;
                 c[I][MT][1] = (8 * I + g < m && 2 * t + 1 < nops) ? r1 : 0.0;
             }

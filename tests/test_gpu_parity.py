@@ -119,7 +119,14 @@ def test_weights_vs_oracle(ctx, oracle, d, g, p, deg, n, ops):
 @pytest.mark.parametrize("d,g,p,deg,n,ops", [
     (2, 50, 5, 3, 30, ["Lap"]), (2, 50, 5, 3, 30, ["E", "Dx", "Dy", "Dxx", "Dyy", "Dxy", ("Dk", 0, 4), ("Dk", 1, 4)]),
     (2, 40, 3, 3, 20, ["E", "Dx", "Dy"]), (2, 40, 7, 2, 33, ["Lap", "Dxy"]), (2, 40, 5, 4, 31, ["Dxx"]),
-    (3, 12, 5, 2, 36, ["Lap", "Dx", "Dy", "Dz"]), (3, 12, 3, 1, 18, ["Dzz", "Dxz"])])
+    (3, 12, 5, 2, 36, ["Lap", "Dx", "Dy", "Dz"]), (3, 12, 3, 1, 18, ["Dzz", "Dxz"]),
+    # multi-warp kernel (weights_mw.cu): 48 < m <= 96
+    (2, 30, 5, 3, 46, ["Lap", "Dx"]),                                                   # m = 56: MT 7, 2 warps
+    (2, 36, 5, 5, 42, ["E", "Dx", "Dy", "Dxx", "Dyy", "Dxy", ("Dk", 0, 4), ("Dk", 1, 4)]),   # m = 63: MT 8 (padded), 2 warps
+    (2, 36, 5, 4, 50, ["Dxx", "Dyy", ("Dk", 0, 4), ("Dk", 1, 4)]),                     # m = 65: MT 9, 4 warps (config 3)
+    (3, 14, 7, 3, 60, ["Lap", "Dx", "Dy", "Dz"]),                                       # m = 80: MT 10, 4 warps (config 4)
+    (2, 30, 7, 5, 66, ["Lap"]),                                                         # m = 87: MT 11
+    (3, 11, 5, 4, 58, ["Lap", "Dz"])])                                                  # m = 93: MT 12
 def test_dmma_kernel_vs_generic_and_oracle(ctx, oracle, d, g, p, deg, n, ops):
     """kernel=2 forces the register/DMMA Gauss-Jordan kernel, kernel=1 the shared-memory LU kernel."""
     X = rb.nodes.jittered_lattice(d, g, seed=8)
@@ -134,7 +141,7 @@ def test_dmma_kernel_vs_generic_and_oracle(ctx, oracle, d, g, p, deg, n, ops):
 def test_dmma_kernel_scope(ctx):
     X = rb.nodes.jittered_lattice(2, 30, seed=1)
     with pytest.raises(rb.RbffdError) as e:
-        rb.generate_raw(X, None, 5, 42, 5, ["Lap"], ctx=ctx, kernel=2)      # m = 63 > 48: generic kernel only
+        rb.generate_raw(X, None, 7, 80, 5, ["Lap"], ctx=ctx, kernel=2)      # m = 101 > 96: generic kernel only
     assert e.value.code == rb._lib.ERR_UNSUPPORTED
     Xd = X.copy()
     Xd[5] = Xd[6]
