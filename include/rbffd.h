@@ -158,6 +158,18 @@ typedef struct {
 int rbffd_rhs_advdiff_device(rbffd_operator* op, const rbffd_advdiff_params* prm, const double* u, double* du);
 int rbffd_rhs_advdiff_host(rbffd_operator* op, const rbffd_advdiff_params* prm, const double* u, double* du);
 
+/* ---- ghost-node boundary updates of cons_sys (examples/adv_diff_test.jl:118-141 set-up, :162-176 per call) ---- */
+/* nb boundaries, applied in the given order.  kind[b] = 1: u[ghost_b] = -inv(D[bc_b, ghost_b]) * (D[bc_b, non-ghost_b] * u)
+ * with D = matrix which[b] of `op` (Dx for left/right, Dy for top/bottom in the example); kind[b] = 0:
+ * u[bc_b] = u[ghost_b] = value[b] (:166-167).  ptr[nb+1] delimits boundary b's entries in bc_idx / ghost_idx
+ * (|ghost_b| == |bc_b|, src/processmesh.jl:174).  Host int64 indices with index_base; u is a device / host vector. */
+typedef struct rbffd_bc rbffd_bc;
+int rbffd_bc_create(rbffd_operator* op, int32_t nb, const int32_t* kind, const int32_t* which, const double* value,
+                    const int64_t* ptr, const int64_t* bc_idx, const int64_t* ghost_idx, int32_t index_base, rbffd_bc** bc);
+int rbffd_bc_apply_device(rbffd_bc* bc, double* u);
+int rbffd_bc_apply_host(rbffd_bc* bc, double* u);
+int rbffd_bc_destroy(rbffd_bc* bc);
+
 /* rows [row0, row1) only, reading x through `xmap` is not needed: sharded operators store LOCAL column
  * ids into [owned | halo]; pack/unpack kernels move halo values (multi-GPU SpMV). */
 int rbffd_gather_device(rbffd_context* ctx, const double* src, const int32_t* index, int64_t count, double* dst);

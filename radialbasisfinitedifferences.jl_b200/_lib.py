@@ -79,6 +79,10 @@ _SIGNATURES = {
     "rbffd_spmv_t_host": ([_vp, _i32, _dbl, _vp, _dbl, _vp], C.c_int),
     "rbffd_rhs_advdiff_device": ([_vp, C.POINTER(AdvDiffParams), _vp, _vp], C.c_int),
     "rbffd_rhs_advdiff_host": ([_vp, C.POINTER(AdvDiffParams), _vp, _vp], C.c_int),
+    "rbffd_bc_create": ([_vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _i32, C.POINTER(_vp)], C.c_int),
+    "rbffd_bc_apply_device": ([_vp, _vp], C.c_int),
+    "rbffd_bc_apply_host": ([_vp, _vp], C.c_int),
+    "rbffd_bc_destroy": ([_vp], C.c_int),
     "rbffd_gather_device": ([_vp, _vp, _vp, _i64, _vp], C.c_int),
     "rbffd_scatter_add_device": ([_vp, _vp, _vp, _i64, _vp], C.c_int),
     "rbffd_jittered_lattice_device": ([_vp, _i32, _i64, C.c_uint64, _i64, _i64, _vp], C.c_int),

@@ -243,6 +243,51 @@ class Operator:
         self.ctx._check(self.ctx._L.rbffd_rhs_advdiff_device(self._h, C.byref(params), u_ptr, du_ptr))
 
 
+class BoundaryConditions:
+    """Ghost-node updates of cons_sys (examples/adv_diff_test.jl:118-141,162-176), device resident.
+
+    boundaries: list of dicts in application order, each {"bc": indices, "ghost": indices, and either
+    "matrix": index of D_b in the operator (ghost values solve (D_b u)[bc] = 0) or "value": Dirichlet value}."""
+
+    def __init__(self, op: Operator, boundaries, index_base=0):
+        self.op = op
+        nb = len(boundaries)
+        kind = np.array([1 if "matrix" in b else 0 for b in boundaries], np.int32)
+        which = np.array([b.get("matrix", 0) for b in boundaries], np.int32)
+        value = np.array([b.get("value", 0.0) for b in boundaries], np.float64)
+        bcs = [np.asarray(b["bc"], np.int64).ravel() for b in boundaries]
+        ghs = [np.asarray(b["ghost"], np.int64).ravel() for b in boundaries]
+        for a, g in zip(bcs, ghs):
+            if a.shape != g.shape:
+                raise ValueError("DimensionMismatch: every boundary needs as many ghost nodes as boundary nodes")
+        ptr = np.concatenate([[0], np.cumsum([len(a) for a in bcs])]).astype(np.int64)
+        bc_idx = np.ascontiguousarray(np.concatenate(bcs)) if nb else np.zeros(0, np.int64)
+        gh_idx = np.ascontiguousarray(np.concatenate(ghs)) if nb else np.zeros(0, np.int64)
+        h = C.c_void_p()
+        op.ctx._check(op.ctx._L.rbffd_bc_create(op._h, nb, _ptr(kind), _ptr(which), _ptr(value), _ptr(ptr), _ptr(bc_idx),
+                                                _ptr(gh_idx), index_base, C.byref(h)))
+        self._h = h
+
+    def apply(self, u):
+        u = np.ascontiguousarray(u, np.float64)
+        self.op.ctx._check(self.op.ctx._L.rbffd_bc_apply_host(self._h, _ptr(u)))
+        return u
+
+    def apply_device(self, u_ptr):
+        self.op.ctx._check(self.op.ctx._L.rbffd_bc_apply_device(self._h, u_ptr))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.op.ctx._L.rbffd_bc_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 _default_ctx = None
 
 

@@ -283,3 +283,90 @@ def test_device_resident_pipeline_and_lattice(ctx, oracle):
     sub = np.random.default_rng(0).choice(N, 2000, replace=False)
     rcol = oracle.knn(Xh, Xh[sub], 30)[0]
     assert np.array_equal(colind[sub], rcol)
+
+
+def test_ghost_node_boundary_updates(ctx):
+    """K7: the ghost updates of cons_sys (examples/adv_diff_test.jl:118-141, 162-176) against a NumPy restatement
+    of those lines (sparse slicing + dense inv), on a synthetic rectangle with boundary and ghost node sets."""
+    import scipy.sparse as sp
+    g = 40
+    h = 1.0 / g
+    X_in = rb.nodes.jittered_lattice(2, g, seed=12)
+    t = (np.arange(g) + 0.5) * h
+    sides = [(np.stack([np.zeros(g), t], 1), (-1, 0)), (np.stack([np.ones(g), t], 1), (1, 0)),
+             (np.stack([t, np.ones(g)], 1), (0, 1)), (np.stack([t, np.zeros(g)], 1), (0, -1))]      # left, right, top, bottom
+    bc_pts = [s[0] for s in sides]
+    gh_pts = [s[0] + 0.7 * h * np.array(s[1]) for s in sides]
+    X = np.concatenate([X_in] + bc_pts + gh_pts)
+    N, n_in = len(X), len(X_in)
+    idx_bc = [range(n_in + b * g, n_in + (b + 1) * g) for b in range(4)]
+    idx_g = [range(n_in + 4 * g + b * g, n_in + 4 * g + (b + 1) * g) for b in range(4)]
+    E, Dx, Dy, Dxx, Dyy, Dxy = rb.generate_operator(X, X, 3, 20, 3, range(0, n_in), idx_bc, idx_g, None, None, None, ctx=ctx, shape="full")
+    colind, vals = rb.generate_raw(X, None, 3, 20, 3, ["Dx", "Dy"], groups=rb.groups_from_index_sets(N, range(0, n_in), idx_bc, idx_g), ctx=ctx)
+    op = rb.Operator.from_host(ctx, colind, vals, N)
+    # application order of the reference: right (Dx), left (Dirichlet 1.0), top (Dy), bottom (Dy)
+    order = [(1, 0), (0, None), (2, 1), (3, 1)]
+    bcs = rb.BoundaryConditions(op, [{"bc": list(idx_bc[b]), "ghost": list(idx_g[b]), **({"matrix": m} if m is not None else {"value": 1.0})}
+                                     for b, m in order])
+    rng = np.random.default_rng(3)
+    u0 = rng.standard_normal(N)
+    got = bcs.apply(u0.copy())
+    # NumPy restatement of adv_diff_test.jl:118-141,162-176
+    ref = u0.copy()
+    D = {0: sp.csr_matrix(Dx), 1: sp.csr_matrix(Dy)}
+    for b, m in order:
+        bc, gh = np.array(idx_bc[b]), np.array(idx_g[b])
+        if m is None:
+            ref[bc] = 1.0
+            ref[gh] = 1.0
+            continue
+        w_g = D[m][bc][:, gh].toarray()
+        rest = np.setdiff1d(np.arange(N), gh)
+        w_int = D[m][bc][:, rest]
+        ref[gh] = -np.linalg.inv(w_g) @ (w_int @ ref[rest])
+    assert np.max(np.abs(got - ref)) <= 1e-10 * np.max(np.abs(ref))
+    # the constraint the ghost values enforce: (D_b u)[bc_b] = 0 on the last-applied boundary
+    assert np.max(np.abs((D[1] @ got)[np.array(idx_bc[3])])) <= 1e-8 * np.abs(D[1]).max()
+
+
+def test_device_resident_time_stepping_example(oracle):
+    """examples/adv_diff_b200.py (generate -> RHS -> ghost updates -> SSP-RK3, all on the device) against the same
+    scheme driven by the CPU oracle's operators and a NumPy restatement of the ghost updates."""
+    import importlib.util, os
+    import scipy.sparse as sp
+    spec = importlib.util.spec_from_file_location("adv_diff_b200", os.path.join(os.path.dirname(__file__), "..", "examples", "adv_diff_b200.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    gy, steps = 16, 12
+    X, u, (idx_in, idx_bc, idx_g) = mod.run(gy=gy, steps=steps, verbose=False)
+    N, n, h = len(X), 42, 1.0 / gy
+    groups = ((idx_in.start, idx_in.stop), [(r.start, r.stop) for r in idx_bc], [(r.start, r.stop) for r in idx_g])
+    names = ["E", "Dx", "Dy", "Dxx", "Dyy", ("Dk", 0, 4), ("Dk", 1, 4)]
+    colind, vals = oracle.generate_operator(X, X, 5, n, 5, groups=groups, ops=names, mode=0)
+    D = [sp.csr_matrix((v.ravel(), colind.ravel(), np.arange(0, N * n + 1, n)), shape=(N, N)) for v in vals]
+    gamma, dt = 100.0 * h ** 4, 0.0025 * h * h
+
+    def cons_sys(uu):                                  # adv_diff_test.jl:144-188 (du from u, then the ghost updates mutate u)
+        du = oracle.rhs_advdiff(colind, *vals, 1.0, 0.0, 0.0, gamma, uu)
+        for b, m in [(1, 1), (0, None), (2, 2), (3, 2)]:
+            bc, gh = np.array(idx_bc[b]), np.array(idx_g[b])
+            if m is None:
+                uu[bc] = 1.0
+                uu[gh] = 1.0
+                continue
+            rest = np.setdiff1d(np.arange(N), gh)
+            uu[gh] = -np.linalg.inv(D[m][bc][:, gh].toarray()) @ (D[m][bc][:, rest] @ uu[rest])
+        return du
+
+    ur = np.where((X[:, 0] - 0.5) ** 2 + (X[:, 1] - 0.5) ** 2 <= 0.04, 10.0, 1.0)
+    for _ in range(steps):
+        du = cons_sys(ur)
+        u1 = ur + dt * du
+        du = cons_sys(u1)
+        u2 = 0.75 * ur + 0.25 * (u1 + dt * du)
+        du = cons_sys(u2)
+        ur = ur / 3.0 + (2.0 / 3.0) * (u2 + dt * du)
+    assert np.all(np.isfinite(u))
+    assert np.max(np.abs(u - ur)) <= 1e-8 * np.max(np.abs(ur))
+    # Dirichlet nodes are re-imposed at the start of every RHS call (adv_diff_test.jl:166-167), so they drift by O(dt) in between
+    assert np.allclose(u[np.array(idx_bc[0])], 1.0, atol=1e-2)
