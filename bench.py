@@ -215,6 +215,11 @@ def main():
     u = torch.randn(NL, dtype=torch.float64, device=dev)
     y = torch.empty(M, dtype=torch.float64, device=dev)
     op = ctx.operator_from_device(M, NL, n, r, colind.data_ptr(), vals.data_ptr())
+    # N > 1: rows that cannot reference halo columns are applied while the halo exchange is in flight
+    parts = []
+    if world > 1:
+        for (r0, r1) in rb.boundary_row_ranges(shard):
+            parts.append((r0, r1, ctx.operator_from_device(r1 - r0, NL, n, 1, colind[r0:].data_ptr(), vals[0, r0:].data_ptr()) if r1 > r0 else None))
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
     phase = {"knn": 0.0, "weights": 0.0, "spmv": 0.0}
 
@@ -230,8 +235,17 @@ def main():
                            Y_ptr=Yown.data_ptr(), M=M, center_ptr=center.data_ptr() if world == 1 else None, NS=M)
         ev[2].record(stream)
         if world > 1:
-            rb.exchange_halo(u, shard)
-        op.spmv_device(0, u.data_ptr(), y.data_ptr())
+            work = rb.exchange_halo(u, shard, async_op=True)
+            (l0, l1, opl), (i0, i1, opi), (h0, h1, oph) = parts
+            if opi is not None:
+                opi.spmv_device(0, u.data_ptr(), y[i0:].data_ptr())          # interior rows overlap the NVLink transfer
+            work.wait()
+            if opl is not None:
+                opl.spmv_device(0, u.data_ptr(), y[l0:].data_ptr())
+            if oph is not None:
+                oph.spmv_device(0, u.data_ptr(), y[h0:].data_ptr())
+        else:
+            op.spmv_device(0, u.data_ptr(), y.data_ptr())
         ev[3].record(stream)
         if record:
             ev[3].synchronize()
@@ -256,6 +270,12 @@ def main():
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)
         if flag.item() != 1:
             raise SystemExit("halo too narrow for exact stencils: increase halo_rows")
+        # rows applied during the exchange must not reference halo columns (exactness of the overlap)
+        (i0, i1) = rb.boundary_row_ranges(shard)[1]
+        if i1 > i0:
+            ci = colind[i0:i1]
+            if int(ci.min()) < shard.n_lo or int(ci.max()) >= shard.n_lo + shard.n_owned:
+                raise SystemExit("interior rows reference halo columns: widen the boundary row ranges")
     launches0 = ctx.launch_count()
     t_start = torch.cuda.Event(enable_timing=True)
     t_end = torch.cuda.Event(enable_timing=True)

@@ -90,13 +90,26 @@ class SlabShard:
         return ok
 
 
-def exchange_halo(u_local, shard: SlabShard, group=None):
+class _HaloWork:
+    """handle of an in-flight halo exchange: wait() makes the current stream (or the host under gloo) wait for it"""
+
+    def __init__(self, reqs):
+        self.reqs = reqs
+
+    def wait(self):
+        for r in self.reqs:
+            r.wait()
+
+
+def exchange_halo(u_local, shard: SlabShard, group=None, async_op=False):
     """Fill the halo parts of u_local = [halo_lo | owned | halo_hi] (1-D torch tensor) from the neighbouring ranks.
-    The owned part must be current.  One batched send/recv group per call (ncclGroupStart/End under NCCL)."""
+    The owned part must be current.  One batched send/recv group per call (ncclGroupStart/End under NCCL).
+    async_op=True returns a handle immediately so that rows which do not touch the halo can be applied while the
+    exchange is in flight (NCCL runs it on its own stream); call .wait() before the boundary rows."""
     import torch.distributed as dist
     s = shard
     if s.world == 1:
-        return u_local
+        return _HaloWork([]) if async_op else u_local
     ops = []
     o0, o1 = s.n_lo, s.n_lo + s.n_owned
     if s.rank > 0:
@@ -108,6 +121,17 @@ def exchange_halo(u_local, shard: SlabShard, group=None):
         above = SlabShard(s.rank + 1, s.world, s.dim, s.g, s.halo_rows)
         ops.append(dist.P2POp(dist.isend, u_local[o1 - above.n_lo:o1], s.rank + 1, group))
         ops.append(dist.P2POp(dist.irecv, u_local[o1:o1 + s.n_hi], s.rank + 1, group))
-    for r in dist.batch_isend_irecv(ops):
-        r.wait()
+    work = _HaloWork(dist.batch_isend_irecv(ops))
+    if async_op:
+        return work
+    work.wait()
     return u_local
+
+
+def boundary_row_ranges(shard: SlabShard):
+    """Owned rows split into (low boundary, interior, high boundary) half-open ranges: only rows within halo_rows
+    lattice rows of a slab face can reference halo columns (that is what halo_is_sufficient verified)."""
+    s = shard
+    lo = min(s.n_owned, s.n_lo)                      # n_lo == halo_rows * row_size when a lower neighbour exists
+    hi = min(s.n_owned - lo, s.n_hi)
+    return (0, lo), (lo, s.n_owned - hi), (s.n_owned - hi, s.n_owned)

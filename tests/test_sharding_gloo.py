@@ -33,6 +33,14 @@ def test_slab_partition_covers_lattice():
                 assert full[s.first_local_id + s.n_local:, -1].min() >= above
 
 
+def test_boundary_row_ranges():
+    for world, rank in ((4, 0), (4, 2), (4, 3), (1, 0)):
+        s = rb.SlabShard(rank, world, 2, 40, 3)
+        (a0, a1), (b0, b1), (c0, c1) = rb.boundary_row_ranges(s)
+        assert a0 == 0 and a1 == b0 and b1 == c0 and c1 == s.n_owned
+        assert a1 - a0 == s.n_lo and c1 - c0 == s.n_hi
+
+
 def test_halo_sufficiency_check(oracle):
     dim, g, world = 2, 40, 2
     full = rb.nodes.jittered_lattice(dim, g, 0)
@@ -60,6 +68,10 @@ def _worker(rank, world, port, dim, g, halo):
     u[s.n_lo:s.n_lo + s.n_owned] = gid[s.n_lo:s.n_lo + s.n_owned] * 3.0 + 1.0      # owned values: f(global id)
     rbw.exchange_halo(u, s)
     ok = torch.equal(u, gid * 3.0 + 1.0)
+    u[:s.n_lo] = -1.0
+    u[s.n_lo + s.n_owned:] = -1.0
+    rbw.exchange_halo(u, s, async_op=True).wait()
+    ok = ok and torch.equal(u, gid * 3.0 + 1.0)
     flag = torch.tensor([1 if ok else 0])
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     dist.destroy_process_group()
