@@ -90,6 +90,8 @@ int rbffd_create(int device, rbffd_context** out) {
     ctx->device = device;
     e = cudaSetDevice(device);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
+    for (int i = 0; i < 4 && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&ctx->chunk_ev[i], cudaEventDisableTiming);
     if (e == cudaSuccess) {
         ctx->own_stream = true;
         for (int i = 0; i < 8 && e == cudaSuccess; ++i) e = cudaEventCreate(&ctx->ev[i]);
@@ -118,6 +120,8 @@ int rbffd_destroy(rbffd_context* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     for (int i = 0; i < 8; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+    for (int i = 0; i < 4; ++i) if (ctx->chunk_ev[i]) cudaEventDestroy(ctx->chunk_ev[i]);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return RBFFD_OK;
@@ -259,6 +263,56 @@ int rbffd_generate_operator_host(rbffd_context* ctx, const rbffd_options* opts, 
     if (xgroup) {
         CUDA_TRY(ctx, dG.alloc(N, st));
         CUDA_TRY(ctx, cudaMemcpyAsync(dG.p, xgroup, sizeof(int32_t) * N, cudaMemcpyHostToDevice, st));
+    }
+    // Collocated rows with pinned output buffers: the rows are generated in chunks and every finished chunk is copied
+    // to the host on a second stream while the next chunk is being solved (the 480 MB D2H of config 2 costs more than
+    // the kernels).  Anything else takes the one-shot path.
+    cudaPointerAttributes pa_c, pa_v;
+    const bool pinned = cudaPointerGetAttributes(&pa_c, colind_out) == cudaSuccess && pa_c.type == cudaMemoryTypeHost &&
+                        cudaPointerGetAttributes(&pa_v, vals_out) == cudaSuccess && pa_v.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    const int nchunks = 8;
+    if (pinned && Y == X && M == N && M >= 64 * nchunks && !opts->sort_columns) {
+        for (int i = 0; i < 8; ++i) ctx->timings[i] = 0.0;
+        const int nops = opts->nops;
+        DevBuf<int32_t> stencils;
+        CUDA_TRY(ctx, stencils.alloc((size_t)N * n, st));
+        RBFFD_TRY(rbffd_stencils_impl(ctx, dX.p, N, dim, dX.p, N, n, xgroup ? dG.p : nullptr, stencils.p, nullptr, nullptr, nullptr));
+        const int64_t ch = ((M + nchunks - 1) / nchunks + 31) / 32 * 32;
+        DevBuf<int32_t> c32[2];
+        DevBuf<int64_t> c64[2];
+        DevBuf<double> vb[2];
+        for (int b = 0; b < 2; ++b) {
+            CUDA_TRY(ctx, c32[b].alloc((size_t)ch * n, st));
+            CUDA_TRY(ctx, c64[b].alloc((size_t)ch * n, st));
+            CUDA_TRY(ctx, vb[b].alloc((size_t)ch * n * nops, st));
+        }
+        CUDA_TRY(ctx, cudaStreamSynchronize(st));
+        double t_weights = 0.0;
+        int rc = RBFFD_OK;
+        int c = 0;
+        for (int64_t r0 = 0; r0 < M && rc == RBFFD_OK; r0 += ch, ++c) {
+            const int64_t cnt = std::min<int64_t>(ch, M - r0);
+            const int b = c & 1;
+            if (c >= 2) CUDA_TRY(ctx, cudaStreamWaitEvent(st, ctx->chunk_ev[b], 0));       // buffer b is free again
+            rc = rbffd_weights_impl(ctx, opts, dX.p, N, dX.p + r0 * dim, cnt, stencils.p + r0 * n, cnt, nullptr, c32[b].p, vb[b].p);
+            t_weights += ctx->timings[3];
+            if (rc != RBFFD_OK) break;
+            // weights_impl has synchronised `st`: chunk c is complete; ship it on the copy stream
+            i32_to_i64_kernel<<<ceil_div_i64(cnt * n, 256), 256, 0, ctx->copy_stream>>>(c32[b].p, cnt * n, opts->index_base, c64[b].p);
+            KLAUNCH(ctx);
+            CUDA_TRY(ctx, cudaMemcpyAsync(colind_out + r0 * n, c64[b].p, sizeof(int64_t) * cnt * n, cudaMemcpyDeviceToHost, ctx->copy_stream));
+            for (int o = 0; o < nops; ++o)
+                CUDA_TRY(ctx, cudaMemcpyAsync(vals_out + ((size_t)o * M + r0) * n, vb[b].p + (size_t)o * cnt * n, sizeof(double) * cnt * n,
+                                              cudaMemcpyDeviceToHost, ctx->copy_stream));
+            CUDA_TRY(ctx, cudaEventRecord(ctx->chunk_ev[b], ctx->copy_stream));
+        }
+        cudaError_t e = cudaStreamSynchronize(ctx->copy_stream);
+        ctx->timings[3] = t_weights;
+        // the stream-ordered temporaries are freed on `st`: make sure the copy stream is done with them first
+        if (rc != RBFFD_OK) return rc;
+        CUDA_TRY(ctx, e);
+        return RBFFD_OK;
     }
     rbffd_operator* op = nullptr;
     RBFFD_TRY(rbffd_operator_generate(ctx, opts, dX.p, N, dYp, M, xgroup ? dG.p : nullptr, &op));

@@ -13,6 +13,8 @@ struct rbffd_context {
     int device = 0;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
+    cudaStream_t copy_stream = nullptr;   // D2H of finished row chunks overlaps the weight kernel of the next chunk
+    cudaEvent_t chunk_ev[4] = {nullptr, nullptr, nullptr, nullptr};
     std::string err;
     double timings[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};

@@ -239,8 +239,7 @@ weights_dmma_mw_kernel(MArgs a) {
 #pragma unroll
                 for (int cc = 0; cc < 4; ++cc) pv[cc] = cv[cc];
                 const double rinv = fast_rcp(pv[sidx]);
-                rinv_s[pr] = rinv;
-                pivcol_s[pr] = 4 * kb + sidx;
+                if (warp == 0) { rinv_s[pr] = rinv; pivcol_s[pr] = 4 * kb + sidx; }   // same value from every lane
                 const bool ispiv = tid == pr;
                 const double nl = ispiv ? 0.0 : av[sidx] * (-rinv);
 #pragma unroll

@@ -370,3 +370,21 @@ def test_device_resident_time_stepping_example(oracle):
     assert np.max(np.abs(u - ur)) <= 1e-8 * np.max(np.abs(ur))
     # Dirichlet nodes are re-imposed at the start of every RHS call (adv_diff_test.jl:166-167), so they drift by O(dt) in between
     assert np.allclose(u[np.array(idx_bc[0])], 1.0, atol=1e-2)
+
+
+def test_chunked_host_path_with_pinned_buffers(ctx):
+    """rbffd_generate_operator_host overlaps the D2H of finished row chunks with the next chunk's solve when the caller's
+    output buffers are pinned; the result must be bit-identical to the one-shot path (pageable buffers)."""
+    import ctypes
+    import torch
+    X = rb.nodes.jittered_lattice(2, 120, seed=21)
+    N, n, ops = len(X), 30, ["Lap", "Dx"]
+    col_ref, val_ref = rb.generate_raw(X, None, 5, n, 3, ops, ctx=ctx)
+    opts = rb.make_options(2, 5, n, 3, ops)
+    Xh = torch.from_numpy(X).pin_memory()
+    ch = torch.empty((N, n), dtype=torch.int64).pin_memory()
+    vh = torch.empty((2, N, n), dtype=torch.float64).pin_memory()
+    ctx._check(ctx._L.rbffd_generate_operator_host(ctx._h, ctypes.byref(opts), ctypes.c_void_p(Xh.data_ptr()), N, None, N, None,
+                                                   ctypes.c_void_p(ch.data_ptr()), ctypes.c_void_p(vh.data_ptr())))
+    assert np.array_equal(ch.numpy(), col_ref)
+    assert np.array_equal(vh.numpy(), val_ref)
