@@ -212,7 +212,12 @@ def main():
     center = torch.empty(M, dtype=torch.int32, device=dev)
     colind = torch.empty((M, n), dtype=torch.int32, device=dev)
     vals = torch.empty((r, M, n), dtype=torch.float64, device=dev)
-    u = torch.randn(NL, dtype=torch.float64, device=dev)
+    # N > 1: the field lives in a CUDA-IPC buffer; neighbours store their boundary rows straight into its halos over
+    # NVLink (csrc/halo.cu).  RBFFD_HALO=nccl selects the torch.distributed send/recv path instead.
+    use_p2p = world > 1 and os.environ.get("RBFFD_HALO", "p2p") != "nccl"
+    halo = rb.PeerHalo(ctx, shard) if use_p2p else None
+    u = halo.field if use_p2p else torch.empty(NL, dtype=torch.float64, device=dev)
+    u.copy_(torch.randn(NL, dtype=torch.float64, device=dev))
     y = torch.empty(M, dtype=torch.float64, device=dev)
     op = ctx.operator_from_device(M, NL, n, r, colind.data_ptr(), vals.data_ptr())
     # N > 1: rows that cannot reference halo columns are applied while the halo exchange is in flight
@@ -235,15 +240,24 @@ def main():
                            Y_ptr=Yown.data_ptr(), M=M, center_ptr=center.data_ptr() if world == 1 else None, NS=M)
         ev[2].record(stream)
         if world > 1:
-            work = rb.exchange_halo(u, shard, async_op=True)
+            work = None
+            if use_p2p:
+                halo.push()
+            else:
+                work = rb.exchange_halo(u, shard, async_op=True)
             (l0, l1, opl), (i0, i1, opi), (h0, h1, oph) = parts
             if opi is not None:
                 opi.spmv_device(0, u.data_ptr(), y[i0:].data_ptr())          # interior rows overlap the NVLink transfer
-            work.wait()
+            if use_p2p:
+                halo.wait()
+            else:
+                work.wait()
             if opl is not None:
                 opl.spmv_device(0, u.data_ptr(), y[l0:].data_ptr())
             if oph is not None:
                 oph.spmv_device(0, u.data_ptr(), y[h0:].data_ptr())
+            if use_p2p:
+                halo.ack()
         else:
             op.spmv_device(0, u.data_ptr(), y.data_ptr())
         ev[3].record(stream)
@@ -300,6 +314,8 @@ def main():
 
     # ---- end to end through the reference-facing host call: pinned host X in, host CSR out, copies inside the timing
     if args.profile:
+        if halo is not None:
+            halo.close()
         if world > 1:
             dist.destroy_process_group()
         return
@@ -358,7 +374,7 @@ def main():
                                     % (args.config - 1, dim, M, p, deg, n, m, r, CFG["ops"])),
                        "step": "exact kNN + fused weight solve -> CSR + one SpMV (halo exchange first if N>1); nodes resident in HBM",
                        "l2": "every step writes %.0f MB of stencils+operator (> 126 MB L2), so no input survives in L2 between steps" % ((M * n * 4 * 2 + r * M * n * 8) / 1e6),
-                       "parallelism": "slab x%d, halo_rows=%d" % (world, halo_rows), "global_nodes": total_nodes},
+                       "parallelism": "slab x%d, halo_rows=%d, halo exchange: %s" % (world, halo_rows, "none" if world == 1 else ("NVLink peer-memory stores (CUDA IPC)" if use_p2p else "NCCL send/recv")), "global_nodes": total_nodes},
             "phases_ms": {"knn": phase["knn"] / K, "weights": phase["weights"] / K, "spmv(+halo)": phase["spmv"] / K},
             "roofline": {"kernel": "weights (fused assemble + pivoted LU + solve + CSR write)", "bound": "fp64",
                          "achieved": ach_w, "peak": fp64_peak, "unit": "TFLOP/s", "frac": ach_w / fp64_peak,
@@ -381,6 +397,8 @@ def main():
                                     "sample": f"{Ns}-node sample (g={args.ref_sample_g}) of the same workload, {dt:.2f} s; CPU oracle = "
                                               "C/OpenMP restatement of the reference (no Julia on the box)"}
         print(json.dumps(line))
+    if halo is not None:
+        halo.close()
     if world > 1:
         dist.destroy_process_group()
 

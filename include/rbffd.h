@@ -175,6 +175,32 @@ int rbffd_bc_destroy(rbffd_bc* bc);
 int rbffd_gather_device(rbffd_context* ctx, const double* src, const int32_t* index, int64_t count, double* dst);
 int rbffd_scatter_add_device(rbffd_context* ctx, const double* src, const int32_t* index, int64_t count, double* dst);
 
+/* ---- NVLink peer-memory halo exchange (one process per GPU) ------------------------------------ */
+/* cudaMalloc + CUDA IPC export / import: the field u = [halo_lo | owned | halo_hi] and its 4 flag words live in such a
+ * buffer so that the neighbouring ranks can store into it directly.  handle64: 64 bytes (cudaIpcMemHandle_t). */
+int rbffd_ipc_alloc(rbffd_context* ctx, int64_t bytes, void** ptr, unsigned char* handle64);
+int rbffd_ipc_free(rbffd_context* ctx, void* ptr);
+int rbffd_ipc_open(rbffd_context* ctx, const unsigned char* handle64, void** peer_ptr);
+int rbffd_ipc_close(rbffd_context* ctx, void* peer_ptr);
+typedef struct {
+    double* u;                 /* my field: n_lo + n_owned + n_hi doubles                                          */
+    int64_t n_lo, n_owned, n_hi;
+    void* flags;               /* my 4 x uint32 flag block (in the same IPC buffer, zero-initialised)               */
+    double* peer_lo_u;         /* lower neighbour's field (mapped peer memory) or NULL                              */
+    void* peer_lo_flags;
+    int64_t peer_lo_offset;    /* where my first rows go in ITS field (= its n_lo + its n_owned)                    */
+    int64_t count_to_lo;       /* = its n_hi                                                                        */
+    double* peer_hi_u;
+    void* peer_hi_flags;
+    int64_t peer_hi_offset;    /* = 0 (its halo_lo)                                                                 */
+    int64_t count_to_hi;       /* = its n_lo                                                                        */
+} rbffd_halo;
+/* epoch = 1, 2, 3, ... (one per exchange, same on every rank).  Call order per application of the operator:
+ * push -> interior rows -> wait -> boundary rows -> ack.  All three are asynchronous kernels on the context's stream. */
+int rbffd_halo_push_device(rbffd_context* ctx, const rbffd_halo* h, uint32_t epoch);
+int rbffd_halo_wait_device(rbffd_context* ctx, const rbffd_halo* h, uint32_t epoch);
+int rbffd_halo_ack_device(rbffd_context* ctx, const rbffd_halo* h, uint32_t epoch);
+
 /* ---- synthetic node sets: jittered lattice in [0,1]^d, counter-based RNG, on device ------ */
 /* node (i,j[,l]) of a g^d lattice, linear ids [first, first+count): ((i,j,l)+0.5+0.5*(U-0.5))/g */
 int rbffd_jittered_lattice_device(rbffd_context* ctx, int32_t dim, int64_t g, uint64_t seed,

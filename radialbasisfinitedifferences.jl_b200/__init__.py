@@ -6,4 +6,4 @@ from ._lib import AdvDiffParams, Options, RbffdError, build, exported_symbols, l
 from .api import (BoundaryConditions, Context, Operator, REFERENCE_OPS, calculateneighbors, default_context, generate_operator,  # noqa: F401
                   generate_raw, groups_from_index_sets, hyperviscosity_operator, make_options)
 from . import nodes  # noqa: F401
-from .sharding import SlabShard, boundary_row_ranges, exchange_halo  # noqa: F401
+from .sharding import PeerHalo, SlabShard, boundary_row_ranges, exchange_halo  # noqa: F401

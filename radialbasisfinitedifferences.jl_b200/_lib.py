@@ -29,6 +29,12 @@ class Options(C.Structure):
                 ("kernel", C.c_int32), ("reserved", C.c_int32 * 5)]
 
 
+class Halo(C.Structure):
+    _fields_ = [("u", C.c_void_p), ("n_lo", C.c_int64), ("n_owned", C.c_int64), ("n_hi", C.c_int64), ("flags", C.c_void_p),
+                ("peer_lo_u", C.c_void_p), ("peer_lo_flags", C.c_void_p), ("peer_lo_offset", C.c_int64), ("count_to_lo", C.c_int64),
+                ("peer_hi_u", C.c_void_p), ("peer_hi_flags", C.c_void_p), ("peer_hi_offset", C.c_int64), ("count_to_hi", C.c_int64)]
+
+
 class AdvDiffParams(C.Structure):
     _fields_ = [("iE", C.c_int32), ("iDx", C.c_int32), ("iDy", C.c_int32), ("iDxx", C.c_int32), ("iDyy", C.c_int32),
                 ("iDxk", C.c_int32), ("iDyk", C.c_int32), ("reserved", C.c_int32),
@@ -83,6 +89,13 @@ _SIGNATURES = {
     "rbffd_bc_apply_device": ([_vp, _vp], C.c_int),
     "rbffd_bc_apply_host": ([_vp, _vp], C.c_int),
     "rbffd_bc_destroy": ([_vp], C.c_int),
+    "rbffd_ipc_alloc": ([_vp, _i64, C.POINTER(_vp), C.c_char_p], C.c_int),
+    "rbffd_ipc_free": ([_vp, _vp], C.c_int),
+    "rbffd_ipc_open": ([_vp, C.c_char_p, C.POINTER(_vp)], C.c_int),
+    "rbffd_ipc_close": ([_vp, _vp], C.c_int),
+    "rbffd_halo_push_device": ([_vp, C.POINTER(Halo), C.c_uint32], C.c_int),
+    "rbffd_halo_wait_device": ([_vp, C.POINTER(Halo), C.c_uint32], C.c_int),
+    "rbffd_halo_ack_device": ([_vp, C.POINTER(Halo), C.c_uint32], C.c_int),
     "rbffd_gather_device": ([_vp, _vp, _vp, _i64, _vp], C.c_int),
     "rbffd_scatter_add_device": ([_vp, _vp, _vp, _i64, _vp], C.c_int),
     "rbffd_jittered_lattice_device": ([_vp, _i32, _i64, C.c_uint64, _i64, _i64, _vp], C.c_int),

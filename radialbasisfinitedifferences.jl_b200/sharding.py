@@ -135,3 +135,78 @@ def boundary_row_ranges(shard: SlabShard):
     lo = min(s.n_owned, s.n_lo)                      # n_lo == halo_rows * row_size when a lower neighbour exists
     hi = min(s.n_owned - lo, s.n_hi)
     return (0, lo), (lo, s.n_owned - hi), (s.n_owned - hi, s.n_owned)
+
+
+class PeerHalo:
+    """NVLink peer-memory halo exchange (csrc/halo.cu): the field lives in a CUDA-IPC buffer, the neighbours store their
+    boundary values straight into its halo regions and publish an epoch flag; no NCCL call on the data path.
+
+        halo = PeerHalo(ctx, shard)          # collective: exchanges IPC handles through torch.distributed
+        u = halo.field                       # torch view [halo_lo | owned | halo_hi] of the IPC buffer
+        halo.push(); <interior rows>; halo.wait(); <boundary rows>; halo.ack()
+    """
+
+    def __init__(self, ctx, shard: SlabShard, group=None):
+        import ctypes as C
+        import torch
+        import torch.distributed as dist
+        from ._lib import Halo
+        self.ctx, self.shard, self.epoch = ctx, shard, 0
+        s = shard
+        nbytes = s.n_local * 8 + 64
+        ptr = C.c_void_p()
+        handle = C.create_string_buffer(64)
+        ctx._check(ctx._L.rbffd_ipc_alloc(ctx._h, nbytes, C.byref(ptr), handle))
+        self._ptr = ptr.value
+        self._peers = []
+        handles = [None] * s.world
+        dist.all_gather_object(handles, bytes(handle.raw), group=group)
+
+        def open_peer(r):
+            p = C.c_void_p()
+            ctx._check(ctx._L.rbffd_ipc_open(ctx._h, handles[r], C.byref(p)))
+            self._peers.append(p.value)
+            return p.value
+
+        h = Halo()
+        h.u, h.n_lo, h.n_owned, h.n_hi = self._ptr, s.n_lo, s.n_owned, s.n_hi
+        h.flags = self._ptr + s.n_local * 8
+        if s.rank > 0:
+            below = SlabShard(s.rank - 1, s.world, s.dim, s.g, s.halo_rows)
+            base = open_peer(s.rank - 1)
+            h.peer_lo_u, h.peer_lo_flags = base, base + below.n_local * 8
+            h.peer_lo_offset, h.count_to_lo = below.n_lo + below.n_owned, below.n_hi
+        if s.rank < s.world - 1:
+            above = SlabShard(s.rank + 1, s.world, s.dim, s.g, s.halo_rows)
+            base = open_peer(s.rank + 1)
+            h.peer_hi_u, h.peer_hi_flags = base, base + above.n_local * 8
+            h.peer_hi_offset, h.count_to_hi = 0, above.n_lo
+        self._h = h
+
+        class _Raw:          # zero-copy torch view of the IPC buffer
+            __cuda_array_interface__ = {"shape": (s.n_local,), "typestr": "<f8", "data": (self._ptr, False), "version": 3, "strides": None}
+        self._raw = _Raw()
+        self.field = torch.as_tensor(self._raw, device=torch.device("cuda", ctx.device))
+        dist.barrier(group=group)
+
+    def push(self):
+        import ctypes as C
+        self.epoch += 1
+        self.ctx._check(self.ctx._L.rbffd_halo_push_device(self.ctx._h, C.byref(self._h), self.epoch))
+
+    def wait(self):
+        import ctypes as C
+        self.ctx._check(self.ctx._L.rbffd_halo_wait_device(self.ctx._h, C.byref(self._h), self.epoch))
+
+    def ack(self):
+        import ctypes as C
+        self.ctx._check(self.ctx._L.rbffd_halo_ack_device(self.ctx._h, C.byref(self._h), self.epoch))
+
+    def close(self):
+        for p in self._peers:
+            self.ctx._L.rbffd_ipc_close(self.ctx._h, p)
+        self._peers = []
+        if self._ptr:
+            self.field = None
+            self.ctx._L.rbffd_ipc_free(self.ctx._h, self._ptr)
+            self._ptr = None

@@ -388,3 +388,19 @@ def test_chunked_host_path_with_pinned_buffers(ctx):
                                                    ctypes.c_void_p(ch.data_ptr()), ctypes.c_void_p(vh.data_ptr())))
     assert np.array_equal(ch.numpy(), col_ref)
     assert np.array_equal(vh.numpy(), val_ref)
+
+
+def test_peer_memory_halo_exchange_two_gpus():
+    """NVLink peer-memory halo exchange + overlapped sharded SpMV (tests/mgpu_halo_check.py) when >= 2 GPUs are visible."""
+    import os
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    here = os.path.dirname(os.path.abspath(__file__))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29577", os.path.join(here, "mgpu_halo_check.py")], capture_output=True, text=True, timeout=300,
+                       env={**os.environ, "HALO_G": "200"})
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "OK" in r.stdout
