@@ -57,7 +57,8 @@ typedef struct {
     int32_t ops[RBFFD_MAX_OPS][4];
     int32_t index_base; /* 0 or 1: base of int64 index arrays crossing the host boundary                */
     int32_t sort_columns; /* != 0: entries of every row sorted by column (CSR form of the CSC the reference builds) */
-    int32_t kernel;     /* 0 = auto, 1 = generic shared-memory LU kernel, 2 = register/DMMA kernel (error if n/a) */
+    int32_t kernel;     /* 0 = auto, 1 = generic shared-memory LU kernel, 2 = register/DMMA Gauss-Jordan kernels,
+                           3 = null-space kernel (2 and 3: error if not applicable) */
     int32_t reserved[5];
 } rbffd_options;
 

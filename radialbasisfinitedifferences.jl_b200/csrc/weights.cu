@@ -405,6 +405,9 @@ __global__ void sort_rows_kernel(int64_t M, int n, int nops, int32_t* __restrict
 // fast path (weights_fast.cu); returns RBFFD_ERR_UNSUPPORTED when the configuration has no fast kernel
 int rbffd_weights_fast(rbffd_context* ctx, const OpTables& T, const double* X, int64_t N, const double* Y, int64_t M,
                        const int32_t* stencils, int32_t* colind_out, double* vals_out, int* fail_flag);
+// null-space path (weights_ns.cu): n <= 32, q <= 12; UNSUPPORTED also when a stencil fails its definiteness check
+int rbffd_weights_ns(rbffd_context* ctx, const OpTables& T, const double* X, int64_t N, const double* Y, int64_t M,
+                     const int32_t* stencils, int32_t* colind_out, double* vals_out, int* fail_flag);
 // multi-warp register/DMMA path for 48 < m <= 96 (weights_mw.cu)
 int rbffd_weights_mw(rbffd_context* ctx, const OpTables& T, const double* X, int64_t N, const double* Y, int64_t M,
                      const int32_t* stencils, int32_t* colind_out, double* vals_out, int* fail_flag);
@@ -448,7 +451,12 @@ int rbffd_weights_impl(rbffd_context* ctx, const rbffd_options* opts, const doub
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev[4], st));
     int rc = RBFFD_ERR_UNSUPPORTED;
     if (identity && opts->kernel != 1) {
-        rc = rbffd_weights_fast(ctx, T, X, N, Y, M, stencils, colind_out, vals_out, flags.p);
+        if (opts->kernel != 2) {
+            rc = rbffd_weights_ns(ctx, T, X, N, Y, M, stencils, colind_out, vals_out, flags.p);
+            if (rc != RBFFD_OK && rc != RBFFD_ERR_UNSUPPORTED) return rc;
+            if (opts->kernel == 3 && rc != RBFFD_OK) RBFFD_FAIL(ctx, RBFFD_ERR_UNSUPPORTED, "null-space kernel not applicable (n=%d, q=%d) or a stencil failed its definiteness check", T.n, T.q);
+        }
+        if (rc == RBFFD_ERR_UNSUPPORTED) rc = rbffd_weights_fast(ctx, T, X, N, Y, M, stencils, colind_out, vals_out, flags.p);
         if (rc == RBFFD_ERR_UNSUPPORTED) rc = rbffd_weights_mw(ctx, T, X, N, Y, M, stencils, colind_out, vals_out, flags.p);
         if (rc != RBFFD_OK && rc != RBFFD_ERR_UNSUPPORTED) return rc;
     }

@@ -138,6 +138,33 @@ def test_dmma_kernel_vs_generic_and_oracle(ctx, oracle, d, g, p, deg, n, ops):
     _check_weights(v1, rvals, cond, ops)
 
 
+@pytest.mark.parametrize("d,g,p,deg,n,ops", [
+    (2, 60, 5, 3, 30, ["Lap"]),                                            # config 2
+    (2, 50, 5, 3, 30, ["E", "Dx", "Dy", "Dxx", "Dyy", "Dxy", ("Dk", 0, 4), ("Dk", 1, 4)]),
+    (2, 40, 3, 3, 20, ["E", "Dx", "Dy", "Dxx", "Dyy", "Dxy"]),             # poisson_test.jl parameters (collocated)
+    (2, 40, 7, 3, 32, ["Lap", "Dxy"]), (2, 40, 5, 2, 18, ["Dxx"]), (2, 40, 3, 1, 9, ["Lap", "Dy"]),
+    (3, 12, 5, 2, 32, ["Lap", "Dx", "Dy", "Dz"]), (3, 12, 3, 1, 12, ["Dzz", "Dxz"])])
+def test_nullspace_kernel_vs_oracle(ctx, oracle, d, g, p, deg, n, ops):
+    """kernel=3 forces the null-space kernel (weights_ns.cu): column reduction of P, DMMA-formed Z'Phi Z, elimination
+    without pivoting.  Same tolerance as every other weight kernel."""
+    X = rb.nodes.jittered_lattice(d, g, seed=8)
+    c3, v3 = rb.generate_raw(X, None, p, n, deg, ops, ctx=ctx, kernel=3)
+    rcol, rvals, cond = oracle.generate_operator(X, X, p, n, deg, ops=ops, mode=0, want_cond=True)
+    assert np.array_equal(c3, rcol)
+    _check_weights(v3, rvals, cond, ops)
+
+
+def test_nullspace_kernel_falls_back_when_not_definite(ctx, oracle):
+    """polydeg < (p-1)/2: Z'Phi Z is not definite, kernel=3 refuses and the automatic dispatch uses the pivoted kernels."""
+    X = rb.nodes.jittered_lattice(2, 30, seed=8)
+    with pytest.raises(rb.RbffdError) as e:
+        rb.generate_raw(X, None, 7, 24, 2, ["Lap"], ctx=ctx, kernel=3)
+    assert e.value.code == rb._lib.ERR_UNSUPPORTED
+    c0, v0 = rb.generate_raw(X, None, 7, 24, 2, ["Lap"], ctx=ctx)
+    rcol, rvals, cond = oracle.generate_operator(X, X, 7, 24, 2, ops=["Lap"], mode=0, want_cond=True)
+    _check_weights(v0, rvals, cond)
+
+
 def test_dmma_kernel_scope(ctx):
     X = rb.nodes.jittered_lattice(2, 30, seed=1)
     with pytest.raises(rb.RbffdError) as e:
