@@ -109,6 +109,9 @@ __global__ void __launch_bounds__(128, 3) weights_ns_kernel(NArgs a) {
 
         // ---- 1. column reduction of [P; g']: lane l < n holds row l of P, lanes o < nops also hold g_o' ----
         double prow[QP], grow[QP];
+        const bool gl = n + nops <= 32;                           // warp-uniform: g rows fit into spare lanes
+        const int go = gl ? lane - n : lane;                      // operator whose g row this lane owns
+        const bool gown = go >= 0 && go < nops;
         {
             prow[0] = lane < n ? 1.0 : 0.0;
 #pragma unroll
@@ -128,12 +131,22 @@ __global__ void __launch_bounds__(128, 3) weights_ns_kernel(NArgs a) {
                 }
                 prow[c] = v;
             }
-#pragma unroll
-            for (int c = 0; c < QP; ++c) {
+            // g rows: lane c evaluates the polynomial right-hand side of monomial c for every operator (the table
+            // walk is per monomial), staged through shared memory so that the row of operator o lands in ONE lane.
+            // With room in the warp (n + nops <= 32) that lane is n + o and g' rides along as an extra row of P.
+            for (int o = 0; o < nops; ++o) {
                 double v = 0.0;
-                if (c < q && lane < nops) v = eta_zero ? rhs_poly_entry_at_zero<D>(T, lane, c, s) : rhs_poly_entry<D>(T, lane, c, eta, s);
-                grow[c] = v;
+                if (lane < q) v = eta_zero ? rhs_poly_entry_at_zero<D>(T, o, lane, s) : rhs_poly_entry<D>(T, o, lane, eta, s);
+                if (lane < QP) WpT[o * QP + lane] = v;           // scratch use of the w_p tile: [op][c]
             }
+            __syncwarp();
+#pragma unroll
+            for (int c = 0; c < QP; c += 2) {
+                const double2 v = gown ? *reinterpret_cast<const double2*>(WpT + go * QP + c) : make_double2(0.0, 0.0);
+                if (gl) { if (gown) { prow[c] = v.x; prow[c + 1] = v.y; } grow[c] = 0.0; grow[c + 1] = 0.0; }
+                else { grow[c] = v.x; grow[c + 1] = v.y; }
+            }
+            __syncwarp();
         }
         bool ok = true;
         bool basic = false;
@@ -148,23 +161,32 @@ __global__ void __launch_bounds__(128, 3) weights_ns_kernel(NArgs a) {
                 const int pl = kmax & 31;
                 if (lane == pl) {
 #pragma unroll
-                    for (int c = 0; c < QP; ++c) Pr[c] = prow[c];
+                    for (int c = 0; c < QP; c += 2) *reinterpret_cast<double2*>(Pr + c) = make_double2(prow[c], prow[c + 1]);
                     basic = true;
                     mybasic = j;
                 }
                 __syncwarp();
                 double pr[QP];
 #pragma unroll
-                for (int c = 0; c < QP; ++c) pr[c] = Pr[c];
+                for (int c = 0; c < QP; c += 2) {
+                    const double2 v = *reinterpret_cast<const double2*>(Pr + c);
+                    pr[c] = v.x;
+                    pr[c + 1] = v.y;
+                }
                 __syncwarp();
                 const double rinv = fast_rcp(pr[j]);
-                const double tl = prow[j] * rinv, tg = grow[j] * rinv;
+                const double tl = prow[j] * rinv;
 #pragma unroll
-                for (int c = 0; c < QP; ++c) {
-                    if (c != j) { prow[c] = fma(-tl, pr[c], prow[c]); grow[c] = fma(-tg, pr[c], grow[c]); }
-                }
+                for (int c = 0; c < QP; ++c)
+                    if (c != j) prow[c] = fma(-tl, pr[c], prow[c]);
                 prow[j] = tl;
-                grow[j] = tg;
+                if (!gl) {                                        // g rows kept in the second register set
+                    const double tg = grow[j] * rinv;
+#pragma unroll
+                    for (int c = 0; c < QP; ++c)
+                        if (c != j) grow[c] = fma(-tg, pr[c], grow[c]);
+                    grow[j] = tg;
+                }
             }
         }
         // positions: non-basic nodes first (0..nb-1, in stencil order), then the basic ones in pivot order
@@ -198,9 +220,9 @@ __global__ void __launch_bounds__(128, 3) weights_ns_kernel(NArgs a) {
             const double rp = rp2 * r2, rp4 = rp2 * fast_rcp(r2);
             for (int o = 0; o < nops; ++o) Bt[pos * 8 + o] = rhs_rbf_entry_fast<D>(T, o, del, s, r, r2, rp, rp2, rp4);
         }
-        if (lane < nops) {
+        if (gown) {
 #pragma unroll
-            for (int c = 0; c < QP; ++c) WpT[c * 8 + lane] = grow[c];
+            for (int c = 0; c < QP; ++c) WpT[c * 8 + go] = gl ? prow[c] : grow[c];
         }
         __syncwarp();
         // ---- 3. Phi~ in permuted order, by symmetric pairs ----
