@@ -226,21 +226,25 @@ __global__ void __launch_bounds__(128, 3) weights_ns_kernel(NArgs a) {
         }
         __syncwarp();
         // ---- 3. Phi~ in permuted order, by symmetric pairs ----
+        // iteration tt pairs row tt with columns tt+1.. (lanes < n-1-tt) and row n-1-tt with columns lane+1 (the
+        // other lanes): every iteration fills n-1 entries, all addresses advance by constants
         {
             const int half = (n + 1) >> 1;
+            const double* __restrict__ Sr = Sc;
+            double* __restrict__ Gw = G;
             for (int tt = 0; tt < half; ++tt) {
-                const int i2 = n - 1 - tt, n1 = n - 1 - tt;
-                for (int cidx = lane; cidx < n - 1; cidx += 32) {
-                    int ia, ib;
-                    if (cidx < n1) { ia = tt; ib = tt + 1 + cidx; }
-                    else { if (i2 == tt) continue; ia = i2; ib = i2 + 1 + (cidx - n1); }
+                const int i2 = n - 1 - tt;
+                const bool first = lane < i2;
+                const int ia = first ? tt : i2;
+                const int ib = first ? tt + 1 + lane : lane + 1;
+                if (lane < n - 1 && (first || i2 != tt)) {
                     double r2 = 0.0;
 #pragma unroll
-                    for (int c = 0; c < D; ++c) { double dd = Sc[ia * D + c] - Sc[ib * D + c]; r2 += dd * dd; }
+                    for (int c = 0; c < D; ++c) { const double dd = Sr[ia * D + c] - Sr[ib * D + c]; r2 = fma(dd, dd, r2); }
                     double v = fast_sqrt(r2);
                     for (int e = 0; e < hp; ++e) v *= r2;
-                    G[ia * LD + ib] = v;
-                    G[ib * LD + ia] = v;
+                    Gw[ia * LD + ib] = v;
+                    Gw[ib * LD + ia] = v;
                 }
             }
         }
