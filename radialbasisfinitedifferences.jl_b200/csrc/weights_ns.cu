@@ -8,15 +8,20 @@
 //      w_p (supported on the basic nodes) of  P' w_p = g ;
 //   2. Z = [-W; I] spans null(P').  PHS r^p is conditionally definite of order (p+1)/2 <= polydeg+1, so
 //      S = Z' Phi Z  is definite ((-1)^((p+1)/2) S is SPD): it is formed with FP64 tensor-core DMMAs
-//      (Y = Phi[:,N] - Phi[:,B] W,  S = Y[N,:] - W' Y[B,:]; the right-hand sides ride along as a fourth tile column)
+//      (Y = Phi[:,N] - Phi[:,B] W,  S = Y[N,:] - W' Y[B,:]; the right-hand sides ride along as extra columns)
 //      and eliminated WITHOUT pivoting;
 //   3. w[N] = S^-1 Z'(b - Phi w_p),  w[B] = w_p - W w[N].
 // Measured against extended precision on the BASELINE stencil families the error is <= 0.06 eps cond(A), the same as
 // pivoted LU; a non-definite S or a rank-deficient P raises a flag and the batch is redone by the
-// Gauss-Jordan kernel (weights_fast.cu).  Work: ~(n-q)^2 (n+q) flops instead of (n+q)^3, 10 pivot searches instead
-// of 40 at config 2, and half the registers, i.e. more resident warps.
-// Scope: collocated rows, n <= 32, q <= 12, n - q <= 24, <= 8 operators, polydeg >= (p-1)/2.
-// Replaces the same reference lines as weights.cu.
+// Gauss-Jordan kernel (weights_fast.cu).  Work: ~(n-q)^2 (n+q) flops instead of (n+q)^3, q pivot searches instead
+// of n+q, and half the registers, i.e. more resident warps.
+//
+// The kernel is specialised at compile time on (dimension, number of monomials): the graded monomial table of
+// build_op_tables (weights.cu) is spelled out as straight-line code, the pivot row of every reduction step travels by
+// SHFL, the right-hand sides ride in the spare columns of the last null-space tile when they fit (nb + nops <= 24),
+// and nothing is zero-filled that a later phase overwrites or never reads.
+// Scope: collocated rows, n <= 32, (d, q) in {(2,3), (2,6), (2,10), (3,4), (3,10)}, n - q <= 24, <= 8 operators,
+// polydeg >= (p-1)/2.   Replaces the same reference lines as weights.cu.
 #include "common.cuh"
 #include "tables.cuh"
 
@@ -31,6 +36,11 @@ struct NArgs {
     double* vals;              // [nops][M][n]
     int* fail;                 // flags[0]: singular node + 1
     int* redo;                 // set to 1 when any stencil needs the pivoted fallback
+    // polynomial right-hand side at eta == 0: DERIV operator o hits exactly one monomial (column gzcol, value alpha!)
+    int32_t gzcol[8];
+    double gzval[8];
+    int32_t bs;                // row stride of the RBF right-hand-side tile (nops rounded up to even)
+    int32_t smem_per_warp;
     OpTables T;
 };
 
@@ -39,199 +49,213 @@ __device__ __forceinline__ void dmma884n(double& c0, double& c1, double a, doubl
                  : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
-constexpr int NS_QP = 12;      // padded polynomial count (3 k-steps of 4)
+// 1/sqrt(x), x > 0, to ~1 ulp: MUFU.RSQ64H seed (relative error ~2^-20) + one third-order step
+// y (1 + e/2 + 3 e^2/8), e = 1 - x y^2
+__device__ __forceinline__ double fast_rsqrt(double x) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double t = x * y;
+    const double e = fma(-t, y, 1.0);
+    double u = fma(e, 0.375, 0.5);
+    u = u * e;
+    return fma(y, u, y);
+}
+
+// max over the warp of a non-negative double: ordering of non-negative doubles == ordering of their bit patterns
+__device__ __forceinline__ double warp_max_nonneg(double v) {
+    const unsigned hi = (unsigned)__double2hiint(v), lo = (unsigned)__double2loint(v);
+    const unsigned hmax = __reduce_max_sync(0xffffffffu, hi);
+    const unsigned lmax = __reduce_max_sync(0xffffffffu, hi == hmax ? lo : 0u);
+    return __hiloint2double((int)hmax, (int)lmax);
+}
+
 constexpr int NS_NB = 24;      // padded null-space dimension (3 tiles)
 constexpr int NS_LD = 33;      // row stride of the Phi tile
 constexpr int NS_US = 34;      // row stride of the Y / [S|t] exchange tile (even: 16-byte rows)
-constexpr int NS_WARPS = 4;
 
-template <int D>
-struct NsCfg {
-    // doubles per warp
-    static constexpr int G = 32 * NS_US;                 // Phi~ (permuted, stride NS_LD); later the Y tile, then the [S|t] tile
-    static constexpr int YB = 0;                         // (Y aliases G)
-    static constexpr int WT = NS_NB * NS_QP;             // W' rows of the non-basic nodes
-    static constexpr int WP = NS_QP * 8;                 // particular solutions, [c][op]
-    static constexpr int BT = 32 * 8;                    // RBF right-hand sides, [pos][op]
-    static constexpr int SC = 32 * D;                    // permuted scaled coordinates
-    static constexpr int PR = NS_QP + 4;                 // pivot-row broadcast buffer
-    static constexpr int YS = 8 * NS_NB;                 // solution y, [op][a]
-    static constexpr int DOUBLES = G + YB + WT + WP + BT + SC + PR + YS;
-    static constexpr int BYTES_PER_WARP = ((DOUBLES * 8 + 32 * 4) + 15) & ~15;   // + perm[32]
-};
+// graded monomials of build_op_tables (weights.cu): mono[t] = mono[mpar[t]] * x[maxis[t]]
+template <int D, int Q>
+__device__ __forceinline__ void mono_row(const double* x, double* m) {
+    m[0] = 1.0;
+    if constexpr (D == 2) {
+        m[1] = x[0]; m[2] = x[1];
+        if constexpr (Q > 3) { m[3] = m[1] * x[0]; m[4] = m[1] * x[1]; m[5] = m[2] * x[1]; }
+        if constexpr (Q > 6) { m[6] = m[3] * x[0]; m[7] = m[3] * x[1]; m[8] = m[4] * x[1]; m[9] = m[5] * x[1]; }
+    } else {
+        m[1] = x[0]; m[2] = x[1]; m[3] = x[2];
+        if constexpr (Q > 4) { m[4] = m[1] * x[0]; m[5] = m[1] * x[1]; m[6] = m[1] * x[2]; m[7] = m[2] * x[1]; m[8] = m[2] * x[2]; m[9] = m[3] * x[2]; }
+    }
+}
+// column of the monomial x_a^2 (the only one with a non-zero Laplacian at 0), -1 when the degree is below 2
+template <int D, int Q>
+__host__ __device__ constexpr int lap_col(int a) {
+    return D == 2 ? (Q > 3 ? (a == 0 ? 3 : 5) : -1) : (Q > 4 ? (a == 0 ? 4 : (a == 1 ? 7 : 9)) : -1);
+}
 
-template <int D>
-__global__ void __launch_bounds__(128, 3) weights_ns_kernel(NArgs a) {
-    using C = NsCfg<D>;
-    constexpr int LD = NS_LD, US = NS_US, QP = NS_QP;
+template <int D, int Q, int MINB>
+__global__ void __launch_bounds__(128, MINB) weights_ns_kernel(NArgs a) {
+    constexpr int LD = NS_LD, US = NS_US;
+    constexpr int KS = (Q + 3) / 4, QP = 4 * KS;      // k-steps of the DMMAs over the basic nodes
     extern __shared__ __align__(16) unsigned char nsm[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = lane >> 2, t = lane & 3;
     const OpTables& T = a.T;
-    const int n = T.n, q = T.q, nops = T.nops, nb = n - q;
-    double* G = reinterpret_cast<double*>(nsm + (size_t)warp * C::BYTES_PER_WARP);
+    const int n = T.n, nops = T.nops, nb = n - Q, BS = a.bs;
+    double* G = reinterpret_cast<double*>(nsm + (size_t)warp * a.smem_per_warp);   // Phi~ (stride LD), then Y, then [S|t]
     double* Yb = G;                                   // aliases G: written only after every read of Phi~ is done
-    double* Wt = G + C::G;
-    double* WpT = Wt + C::WT;
-    double* Bt = WpT + C::WP;
-    double* Sc = Bt + C::BT;
-    double* Pr = Sc + C::SC;
-    double* Ys = Pr + C::PR;
-    int* perm = reinterpret_cast<int*>(Ys + C::YS);
+    double* Wt = G + 32 * US;                         // [32][QP]: W' rows of the non-basic nodes, then the w_p rows
+    double* Bt = Wt + 32 * QP;                        // [32][BS]: RBF right-hand sides by position
+    double* Ys = Bt;                                  // solution y, [op][24] (Bt is dead by then)
+    double* Sc = Bt + 32 * BS;                        // permuted scaled coordinates
+    int* perm = reinterpret_cast<int*>(Sc + 32 * D);
     const double EPS = 2.220446049250313e-16;
     const unsigned FULL = 0xffffffffu;
     const double sgn = (((T.p + 1) >> 1) & 1) ? -1.0 : 1.0;       // (-1)^((p+1)/2) S is positive definite
     const int hp = (T.p - 1) >> 1;
+    // right-hand-side columns: in the spare columns of the last null-space tile when they fit, else in a 4th tile column
+    const int rc0 = (nb + 3) & ~3;
+    const bool fold = rc0 + nops <= NS_NB;
+    const int rcb = fold ? rc0 : NS_NB;               // first right-hand-side column; also the row of w_p in Wt
+    const int NJ = fold ? 3 : 4;
+    const bool gl = n + nops <= 32;                   // g rows fit into spare lanes of the column reduction
+    const int go = gl ? lane - n : lane;              // operator whose g row this lane owns
+    const bool gown = go >= 0 && go < nops;
 
-    for (int64_t i = blockIdx.x * (int64_t)NS_WARPS + warp; i < a.NS; i += (int64_t)gridDim.x * NS_WARPS) {
+    for (int64_t i = blockIdx.x * 4ll + warp; i < a.NS; i += (int64_t)gridDim.x * 4) {
+        // ---- 0. scalestencil.jl:10-20: lane l owns stencil node l ----
         const int32_t* st = a.stencils + i * n;
-        const int c0 = st[0];
-        double xc[D], s[D], sx[D];
-#pragma unroll
-        for (int c = 0; c < D; ++c) xc[c] = a.X[(int64_t)c0 * D + c];
-        // ---- scalestencil.jl:10-20: lane l owns stencil node l ----
-        {
-            const int id = lane < n ? st[lane] : c0;
-            double mx[D];
-#pragma unroll
-            for (int c = 0; c < D; ++c) { sx[c] = a.X[(int64_t)id * D + c] - xc[c]; mx[c] = fabs(sx[c]); }
-#pragma unroll
-            for (int c = 0; c < D; ++c) {
-                for (int o = 16; o > 0; o >>= 1) mx[c] = fmax(mx[c], __shfl_xor_sync(FULL, mx[c], o));
-                s[c] = 1.0 / mx[c];
-                sx[c] = sx[c] * s[c];
-            }
-        }
-        double eta[D];
+        const int id = st[lane < n ? lane : 0];
+        double sx[D], s[D], eta[D];
         bool eta_zero = true;
 #pragma unroll
-        for (int c = 0; c < D; ++c) { eta[c] = (a.Y[i * D + c] - xc[c]) * s[c]; eta_zero = eta_zero && (eta[c] == 0.0); }
-
-        // ---- 1. column reduction of [P; g']: lane l < n holds row l of P, lanes o < nops also hold g_o' ----
-        double prow[QP], grow[QP];
-        const bool gl = n + nops <= 32;                           // warp-uniform: g rows fit into spare lanes
-        const int go = gl ? lane - n : lane;                      // operator whose g row this lane owns
-        const bool gown = go >= 0 && go < nops;
+        for (int c = 0; c < D; ++c) {
+            const double xv = a.X[(int64_t)id * D + c];
+            const double xc = __shfl_sync(FULL, xv, 0);
+            sx[c] = xv - xc;
+            s[c] = 1.0 / warp_max_nonneg(fabs(sx[c]));
+            sx[c] = sx[c] * s[c];
+            eta[c] = (a.Y[i * D + c] - xc) * s[c];
+            eta_zero = eta_zero && (eta[c] == 0.0);
+        }
+        // ---- 1. column reduction of [P; g']: lane l < n holds row l of P, lane n+o (or registers grow) the row g_o' ----
+        double prow[Q], grow[Q];
+        mono_row<D, Q>(sx, prow);
+        if (lane >= n) {
+#pragma unroll
+            for (int c = 0; c < Q; ++c) prow[c] = 0.0;
+        }
         {
-            prow[0] = lane < n ? 1.0 : 0.0;
+            double gv[Q];
+            if (eta_zero) {
+                const int og = gown ? go : 0;
+                const bool lap = T.kind[og] == RBFFD_OP_LAPLACE;
+                const int col = a.gzcol[og];
+                const double val = a.gzval[og];
 #pragma unroll
-            for (int c = 1; c < QP; ++c) {
-                double v = 0.0;
-                if (c < q && lane < n) {
-                    // mono[c] = mono[parent] * x[axis]; parents precede children, so a select chain over the
-                    // already computed entries resolves the (warp-uniform) parent index
-                    const int par = T.mpar[c], ax = T.maxis[c];
-                    double pv = prow[0];
+                for (int c = 0; c < Q; ++c) {
+                    double v = (c == col) ? val : 0.0;
 #pragma unroll
-                    for (int u = 1; u < QP; ++u) if (u < c && u == par) pv = prow[u];
-                    double xa = sx[0];
-#pragma unroll
-                    for (int d2 = 1; d2 < D; ++d2) if (d2 == ax) xa = sx[d2];
-                    v = pv * xa;
+                    for (int ax = 0; ax < D; ++ax)
+                        if (c == lap_col<D, Q>(ax)) v = lap ? 2.0 * s[ax] * s[ax] : v;
+                    gv[c] = v;
                 }
-                prow[c] = v;
-            }
-            // g rows: lane c evaluates the polynomial right-hand side of monomial c for every operator (the table
-            // walk is per monomial), staged through shared memory so that the row of operator o lands in ONE lane.
-            // With room in the warp (n + nops <= 32) that lane is n + o and g' rides along as an extra row of P.
-            for (int o = 0; o < nops; ++o) {
-                double v = 0.0;
-                if (lane < q) v = eta_zero ? rhs_poly_entry_at_zero<D>(T, o, lane, s) : rhs_poly_entry<D>(T, o, lane, eta, s);
-                if (lane < QP) WpT[o * QP + lane] = v;           // scratch use of the w_p tile: [op][c]
-            }
-            __syncwarp();
+            } else {
+                // general evaluation point: lane c evaluates monomial c for every operator, staged through shared
+                // memory so that the row of operator o lands in one lane
+                for (int o = 0; o < nops; ++o) {
+                    const double v = lane < Q ? rhs_poly_entry<D>(T, o, lane, eta, s) : 0.0;
+                    if (lane < Q) Wt[o * QP + lane] = v;
+                }
+                __syncwarp();
 #pragma unroll
-            for (int c = 0; c < QP; c += 2) {
-                const double2 v = gown ? *reinterpret_cast<const double2*>(WpT + go * QP + c) : make_double2(0.0, 0.0);
-                if (gl) { if (gown) { prow[c] = v.x; prow[c + 1] = v.y; } grow[c] = 0.0; grow[c + 1] = 0.0; }
-                else { grow[c] = v.x; grow[c + 1] = v.y; }
+                for (int c = 0; c < Q; ++c) gv[c] = gown ? Wt[go * QP + c] : 0.0;
+                __syncwarp();
             }
-            __syncwarp();
+#pragma unroll
+            for (int c = 0; c < Q; ++c) {
+                if (gl) { if (gown) prow[c] = gv[c]; grow[c] = 0.0; }
+                else grow[c] = gown ? gv[c] : 0.0;
+            }
         }
         bool ok = true;
         bool basic = false;
         int mybasic = 0;
 #pragma unroll
-        for (int j = 0; j < QP; ++j) {
-            if (j < q) {
-                const unsigned hi = (unsigned)__double2hiint(prow[j]) & 0x7fffffe0u;
-                const unsigned key = (lane < n && !basic) ? (hi | (unsigned)lane) : 0u;
-                const unsigned kmax = __reduce_max_sync(FULL, key);
-                if (kmax < 32u) ok = false;                         // P is rank deficient on this stencil
-                const int pl = kmax & 31;
-                if (lane == pl) {
+        for (int j = 0; j < Q; ++j) {
+            const unsigned hi = (unsigned)__double2hiint(prow[j]) & 0x7fffffe0u;
+            const unsigned key = (lane < n && !basic) ? (hi | (unsigned)lane) : 0u;
+            const unsigned kmax = __reduce_max_sync(FULL, key);
+            ok = ok && kmax >= 32u;                             // P is rank deficient on this stencil otherwise
+            const int pl = kmax & 31;
+            if (lane == pl) { basic = true; mybasic = j; }
+            double pr[Q];
 #pragma unroll
-                    for (int c = 0; c < QP; c += 2) *reinterpret_cast<double2*>(Pr + c) = make_double2(prow[c], prow[c + 1]);
-                    basic = true;
-                    mybasic = j;
-                }
-                __syncwarp();
-                double pr[QP];
+            for (int c = 0; c < Q; ++c) pr[c] = __shfl_sync(FULL, prow[c], pl);
+            const double rinv = fast_rcp(pr[j]);
+            const double tl = prow[j] * rinv;
 #pragma unroll
-                for (int c = 0; c < QP; c += 2) {
-                    const double2 v = *reinterpret_cast<const double2*>(Pr + c);
-                    pr[c] = v.x;
-                    pr[c + 1] = v.y;
-                }
-                __syncwarp();
-                const double rinv = fast_rcp(pr[j]);
-                const double tl = prow[j] * rinv;
+            for (int c = 0; c < Q; ++c)
+                if (c != j) prow[c] = fma(-tl, pr[c], prow[c]);
+            prow[j] = tl;
+            if (!gl) {                                          // g rows kept in the second register set
+                const double tg = grow[j] * rinv;
 #pragma unroll
-                for (int c = 0; c < QP; ++c)
-                    if (c != j) prow[c] = fma(-tl, pr[c], prow[c]);
-                prow[j] = tl;
-                if (!gl) {                                        // g rows kept in the second register set
-                    const double tg = grow[j] * rinv;
-#pragma unroll
-                    for (int c = 0; c < QP; ++c)
-                        if (c != j) grow[c] = fma(-tg, pr[c], grow[c]);
-                    grow[j] = tg;
-                }
+                for (int c = 0; c < Q; ++c)
+                    if (c != j) grow[c] = fma(-tg, pr[c], grow[c]);
+                grow[j] = tg;
             }
         }
         // positions: non-basic nodes first (0..nb-1, in stencil order), then the basic ones in pivot order
         const unsigned nbmask = __ballot_sync(FULL, lane < n && !basic);
         const int pos = lane < n ? (basic ? nb + mybasic : __popc(nbmask & ((1u << lane) - 1u))) : 31;
-        // ---- 2. stage W', w_p, permuted coordinates; zero the tiles that are read with padding ----
-        for (int e = lane; e < C::G; e += 32) G[e] = 0.0;
-        for (int e = lane; e < C::WT; e += 32) Wt[e] = 0.0;
-        for (int e = lane; e < C::WP + C::BT; e += 32) WpT[e] = 0.0;      // WpT and Bt are contiguous
-        __syncwarp();
+        // ---- 2. stage W', w_p, permuted coordinates and the RBF right-hand sides ----
+        {
+            // rows of Wt: non-basic node -> its position; g row of operator o -> rcb + o
+            const bool wnb = lane < n && !basic;
+            const int wrow = wnb ? pos : (gown ? rcb + go : -1);
+            if (wrow >= 0) {
+                double2* dst = reinterpret_cast<double2*>(Wt + wrow * QP);
+                const bool useg = !gl && !wnb;
+#pragma unroll
+                for (int c = 0; c < QP; c += 2) {
+                    const double v0 = c < Q ? (useg ? grow[c] : prow[c]) : 0.0;
+                    const double v1 = c + 1 < Q ? (useg ? grow[c + 1] : prow[c + 1]) : 0.0;
+                    dst[c >> 1] = make_double2(v0, v1);
+                }
+            }
+            if (!gl && gown && lane < n && !basic) {            // this lane owns a W' row AND a g row
+                double2* dst = reinterpret_cast<double2*>(Wt + (rcb + go) * QP);
+#pragma unroll
+                for (int c = 0; c < QP; c += 2)
+                    dst[c >> 1] = make_double2(c < Q ? grow[c] : 0.0, c + 1 < Q ? grow[c + 1] : 0.0);
+            }
+        }
         if (lane < n) {
             perm[pos] = lane;
+            G[pos * LD + pos] = 0.0;
 #pragma unroll
             for (int c = 0; c < D; ++c) Sc[pos * D + c] = sx[c];
-            if (!basic) {
-#pragma unroll
-                for (int c = 0; c < QP; ++c) Wt[pos * QP + c] = prow[c];
-            }
             // RBF part of the right-hand sides at this node (generate_operator.jl:123-154)
             double del[D];
             double r2 = 0.0;
 #pragma unroll
             for (int c = 0; c < D; ++c) {
-                double dd = eta[c] - sx[c];
+                const double dd = eta[c] - sx[c];
                 del[c] = dd == 0.0 ? EPS : dd;
-                r2 += del[c] * del[c];
+                r2 = fma(del[c], del[c], r2);
             }
-            const double r = fast_sqrt(r2);
-            double rp2 = T.p >= 3 ? r : fast_rcp(r);
-            for (int e = 1; e < hp; ++e) rp2 *= r2;
-            const double rp = rp2 * r2, rp4 = rp2 * fast_rcp(r2);
-            for (int o = 0; o < nops; ++o) Bt[pos * 8 + o] = rhs_rbf_entry_fast<D>(T, o, del, s, r, r2, rp, rp2, rp4);
-        }
-        if (gown) {
-#pragma unroll
-            for (int c = 0; c < QP; ++c) WpT[c * 8 + go] = gl ? prow[c] : grow[c];
+            const double y = fast_rsqrt(r2);
+            double rp4 = y;                                     // r^(p-4)
+            for (int e = 1; e < hp; ++e) rp4 *= r2;
+            const double rp2 = rp4 * r2, rp = rp2 * r2, r = r2 * y;
+            for (int o = 0; o < nops; ++o) Bt[pos * BS + o] = rhs_rbf_entry_fast<D>(T, o, del, s, r, r2, rp, rp2, rp4);
         }
         __syncwarp();
         // ---- 3. Phi~ in permuted order, by symmetric pairs ----
         // iteration tt pairs row tt with columns tt+1.. (lanes < n-1-tt) and row n-1-tt with columns lane+1 (the
-        // other lanes): every iteration fills n-1 entries, all addresses advance by constants
+        // other lanes): every iteration fills n-1 entries
         {
             const int half = (n + 1) >> 1;
-            const double* __restrict__ Sr = Sc;
-            double* __restrict__ Gw = G;
             for (int tt = 0; tt < half; ++tt) {
                 const int i2 = n - 1 - tt;
                 const bool first = lane < i2;
@@ -240,77 +264,73 @@ __global__ void __launch_bounds__(128, 3) weights_ns_kernel(NArgs a) {
                 if (lane < n - 1 && (first || i2 != tt)) {
                     double r2 = 0.0;
 #pragma unroll
-                    for (int c = 0; c < D; ++c) { const double dd = Sr[ia * D + c] - Sr[ib * D + c]; r2 = fma(dd, dd, r2); }
-                    double v = fast_sqrt(r2);
-                    for (int e = 0; e < hp; ++e) v *= r2;
-                    Gw[ia * LD + ib] = v;
-                    Gw[ib * LD + ia] = v;
+                    for (int c = 0; c < D; ++c) { const double dd = Sc[ia * D + c] - Sc[ib * D + c]; r2 = fma(dd, dd, r2); }
+                    double v = fast_rsqrt(r2);
+                    for (int e = 0; e <= hp; ++e) v *= r2;      // r^p = r2^((p+1)/2) / r
+                    v = r2 > 0.0 ? v : 0.0;
+                    G[ia * LD + ib] = v;
+                    G[ib * LD + ia] = v;
                 }
             }
         }
         __syncwarp();
-        // ---- 4. Y = Phi~[:, N] - Phi~[:, B] W   (4 x 4 tiles; tile column 3 = right-hand sides with w_p) ----
+        // ---- 4. Y = Phi~[:, N] - Phi~[:, B] W   (4 x NJ tiles; the right-hand-side columns start from b and use w_p) ----
         double c[4][4][2];
         {
-            const double* gl = G + g * LD + 2 * t;
-            const double* bl = Bt + g * 8 + 2 * t;
 #pragma unroll
-            for (int I = 0; I < 4; ++I) {
+            for (int J = 0; J < 4; ++J) {
 #pragma unroll
-                for (int J = 0; J < 3; ++J) {
-                    c[I][J][0] = gl[8 * I * LD + 8 * J];
-                    c[I][J][1] = gl[8 * I * LD + 8 * J + 1];
+                for (int e = 0; e < 2; ++e) {
+                    const int col = 8 * J + 2 * t + e;
+                    // source of column `col`: Phi~ (null-space column), b (right-hand side) or zero (G[0] is a zero)
+                    const bool isn = col < nb, isr = col >= rcb && col < rcb + nops;
+                    const double* src = isn ? G + g * LD + col : (isr ? Bt + g * BS + (col - rcb) : G);
+                    const int str = isn ? 8 * LD : (isr ? 8 * BS : 0);
+#pragma unroll
+                    for (int I = 0; I < 4; ++I) c[I][J][e] = J < NJ ? src[I * str] : 0.0;
                 }
-                c[I][3][0] = bl[8 * I * 8];
-                c[I][3][1] = bl[8 * I * 8 + 1];
             }
-            // columns >= nb of the first three tile columns belong to basic nodes: they are not part of Phi~[:, N]
 #pragma unroll
-            for (int I = 0; I < 4; ++I)
-#pragma unroll
-                for (int J = 0; J < 3; ++J)
-#pragma unroll
-                    for (int e = 0; e < 2; ++e)
-                        if (8 * J + 2 * t + e >= nb) c[I][J][e] = 0.0;
-#pragma unroll
-            for (int k = 0; k < 3; ++k) {
+            for (int k = 0; k < KS; ++k) {
                 double af[4], bf[4];
 #pragma unroll
-                for (int I = 0; I < 4; ++I) {
-                    const int col = nb + 4 * k + t;
-                    af[I] = (4 * k + t < q) ? -G[(8 * I + g) * LD + col] : 0.0;
-                }
+                for (int I = 0; I < 4; ++I) af[I] = (4 * k + t < Q) ? -G[(8 * I + g) * LD + nb + 4 * k + t] : 0.0;
 #pragma unroll
-                for (int J = 0; J < 3; ++J) bf[J] = Wt[(8 * J + g) * QP + 4 * k + t];
-                bf[3] = WpT[(4 * k + t) * 8 + g];
+                for (int J = 0; J < 4; ++J) bf[J] = J < NJ ? Wt[(8 * J + g) * QP + 4 * k + t] : 0.0;
 #pragma unroll
-                for (int I = 0; I < 4; ++I)
+                for (int J = 0; J < 4; ++J)
+                    if (J < NJ) {
 #pragma unroll
-                    for (int J = 0; J < 4; ++J) dmma884n(c[I][J][0], c[I][J][1], af[I], bf[J]);
+                        for (int I = 0; I < 4; ++I) dmma884n(c[I][J][0], c[I][J][1], af[I], bf[J]);
+                    }
             }
         }
         // ---- 5. [S | t] = Y[N, :] - W' Y[B, :] ----
         __syncwarp();                                     // Phi~ is dead: the Y tile reuses its storage
 #pragma unroll
-        for (int I = 0; I < 4; ++I)
+        for (int J = 0; J < 4; ++J)
+            if (J < NJ) {
 #pragma unroll
-            for (int J = 0; J < 4; ++J)
-                *reinterpret_cast<double2*>(Yb + (8 * I + g) * US + 8 * J + 2 * t) = make_double2(c[I][J][0], c[I][J][1]);
+                for (int I = 0; I < 4; ++I)
+                    *reinterpret_cast<double2*>(Yb + (8 * I + g) * US + 8 * J + 2 * t) = make_double2(c[I][J][0], c[I][J][1]);
+            }
         __syncwarp();
 #pragma unroll
-        for (int k = 0; k < 3; ++k) {
+        for (int k = 0; k < KS; ++k) {
             double af[3], bf[4];
 #pragma unroll
             for (int I = 0; I < 3; ++I) af[I] = -Wt[(8 * I + g) * QP + 4 * k + t];
 #pragma unroll
-            for (int J = 0; J < 4; ++J) bf[J] = (4 * k + t < q) ? Yb[(nb + 4 * k + t) * US + 8 * J + g] : 0.0;
+            for (int J = 0; J < 4; ++J) bf[J] = (J < NJ && 4 * k + t < Q) ? Yb[(nb + 4 * k + t) * US + 8 * J + g] : 0.0;
 #pragma unroll
-            for (int I = 0; I < 3; ++I)
+            for (int J = 0; J < 4; ++J)
+                if (J < NJ) {
 #pragma unroll
-                for (int J = 0; J < 4; ++J) dmma884n(c[I][J][0], c[I][J][1], af[I], bf[J]);
+                    for (int I = 0; I < 3; ++I) dmma884n(c[I][J][0], c[I][J][1], af[I], bf[J]);
+                }
         }
         __syncwarp();
-        // identity padding outside the nb x nb block
+        // identity padding outside the nb x nb block; right-hand-side columns of padded rows are zero
 #pragma unroll
         for (int I = 0; I < 3; ++I) {
             const int row = 8 * I + g;
@@ -319,7 +339,8 @@ __global__ void __launch_bounds__(128, 3) weights_ns_kernel(NArgs a) {
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
                     const int col = 8 * J + 2 * t + e;
-                    if (row >= nb || col >= nb) c[I][J][e] = row == col ? sgn : 0.0;
+                    if (col >= rcb) { if (row >= nb) c[I][J][e] = 0.0; }
+                    else if (row >= nb || col >= nb) c[I][J][e] = row == col ? sgn : 0.0;
                 }
             if (row >= nb) { c[I][3][0] = 0.0; c[I][3][1] = 0.0; }
         }
@@ -356,7 +377,7 @@ __global__ void __launch_bounds__(128, 3) weights_ns_kernel(NArgs a) {
                     for (int cc = sidx; cc < 4; ++cc) pv[cc] = __shfl_sync(FULL, av[cc], pr);
 #pragma unroll
                     for (int cc = 0; cc < sidx; ++cc) wp[cc] = __shfl_sync(FULL, w[cc], pr);
-                    if (!(sgn * pv[sidx] > 0.0)) ok = false;      // S not definite: the pivoted kernel must take over
+                    ok = ok && (sgn * pv[sidx] > 0.0);    // S not definite: the pivoted kernel must take over
                     const double rinv = fast_rcp(pv[sidx]);
                     if (lane == 0) rinv_s[pr] = rinv;
                     const double nl = lane == pr ? 0.0 : av[sidx] * (-rinv);
@@ -376,7 +397,7 @@ __global__ void __launch_bounds__(128, 3) weights_ns_kernel(NArgs a) {
                     double2* dst = reinterpret_cast<double2*>(Ubuf + (g & 3) * US6 + 2 * t);
 #pragma unroll
                     for (int J = 0; J < 4; ++J)
-                        if (J >= jlo) dst[4 * J] = make_double2(c[Jp][J][0], c[Jp][J][1]);
+                        if (J >= jlo && J < NJ) dst[4 * J] = make_double2(c[Jp][J][0], c[Jp][J][1]);
                 }
                 __syncwarp();
                 double af[3];
@@ -384,7 +405,7 @@ __global__ void __launch_bounds__(128, 3) weights_ns_kernel(NArgs a) {
                 for (int I = 0; I < 3; ++I) af[I] = lb_r[8 * I];
 #pragma unroll
                 for (int J = 0; J < 4; ++J) {
-                    if (J >= jlo) {
+                    if (J >= jlo && J < NJ) {
                         const double bf = ub_r[8 * J];
 #pragma unroll
                         for (int I = 0; I < 3; ++I) dmma884n(c[I][J][0], c[I][J][1], af[I], bf);
@@ -393,20 +414,22 @@ __global__ void __launch_bounds__(128, 3) weights_ns_kernel(NArgs a) {
                 __syncwarp();
             }
         }
-        // y = RHS_row / pivot_row
-        __syncwarp();
+        // y = RHS_row / pivot_row  (right-hand-side column rcb + o lives in tile (rcb + o) / 8)
 #pragma unroll
         for (int I = 0; I < 3; ++I) {
             const int row = 8 * I + g;
-            if (row < nb) {
-                const double ri = rinv_s[row];
+            const double ri = rinv_s[row < nb ? row : 0];
 #pragma unroll
-                for (int e = 0; e < 2; ++e)
-                    if (2 * t + e < nops) Ys[(2 * t + e) * NS_NB + row] = c[I][3][e] * ri;
-            }
+            for (int J = 0; J < 4; ++J)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int o = 8 * J + 2 * t + e - rcb;
+                    if (row < nb && J < NJ && o >= 0 && o < nops) Ys[o * NS_NB + row] = c[I][J][e] * ri;
+                }
         }
         __syncwarp();
         // ---- 7. w[N] = y, w[B] = w_p - W y; rescale and scatter into the CSR row (generate_operator.jl:161-182) ----
+        const int dstj = perm[lane < n ? lane : 0];
         for (int o = 0; o < nops; ++o) {
             const double f = op_post_factor<D>(T, o, s);
             double* vrow = a.vals + ((int64_t)o * a.M + i) * n;
@@ -414,31 +437,53 @@ __global__ void __launch_bounds__(128, 3) weights_ns_kernel(NArgs a) {
             if (lane < nb) wv = Ys[o * NS_NB + lane];
             else if (lane < n) {
                 const int cc = lane - nb;
-                double acc = WpT[cc * 8 + o];
-                for (int aa = 0; aa < nb; ++aa) acc = fma(-Wt[aa * QP + cc], Ys[o * NS_NB + aa], acc);
-                wv = acc;
+                double acc0 = Wt[(rcb + o) * QP + cc], acc1 = 0.0;
+                const double* wcol = Wt + cc;
+                const double* yv = Ys + o * NS_NB;
+                int aa = 0;
+                for (; aa + 1 < nb; aa += 2) {
+                    acc0 = fma(-wcol[aa * QP], yv[aa], acc0);
+                    acc1 = fma(-wcol[(aa + 1) * QP], yv[aa + 1], acc1);
+                }
+                if (aa < nb) acc0 = fma(-wcol[aa * QP], yv[aa], acc0);
+                wv = acc0 + acc1;
             }
-            if (lane < n) vrow[perm[lane]] = ok ? f * wv : nan("");
+            if (lane < n) vrow[dstj] = ok ? f * wv : nan("");
         }
-        for (int j = lane; j < n; j += 32) a.colind[i * n + j] = st[j];
+        if (lane < n) a.colind[i * n + lane] = id;
         if (!ok && lane == 0) *a.redo = 1;
         __syncwarp();
     }
 }
 
-template <int D>
-int launch_ns(rbffd_context* ctx, const NArgs& a) {
-    using C = NsCfg<D>;
-    const size_t smem = (size_t)C::BYTES_PER_WARP * NS_WARPS;
+template <int D, int Q>
+int launch_ns(rbffd_context* ctx, NArgs& a) {
+    constexpr int QP = 4 * ((Q + 3) / 4);
+    a.bs = (a.T.nops + 1) & ~1;
+    a.smem_per_warp = ((32 * NS_US + 32 * QP + 32 * a.bs + 32 * D) * 8 + 32 * 4 + 15) & ~15;
+    const size_t smem = (size_t)a.smem_per_warp * 4;
     if ((int64_t)smem > ctx->max_smem_optin) return RBFFD_ERR_UNSUPPORTED;
-    auto kern = weights_ns_kernel<D>;
+    // 4 CTAs (16 warps) per SM when the shared-memory tile allows it, else 3
+    const bool four = (smem + 1024) * 4 <= 228 * 1024;
+    auto kern = four ? weights_ns_kernel<D, Q, 4> : weights_ns_kernel<D, Q, 3>;
     CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int64_t blocks_needed = (a.NS + NS_WARPS - 1) / NS_WARPS;
-    const int grid = (int)std::min<int64_t>(blocks_needed, (int64_t)ctx->sm_count * 3 * 8);
-    kern<<<grid, NS_WARPS * 32, smem, ctx->stream>>>(a);
+    const int64_t blocks_needed = (a.NS + 3) / 4;
+    const int grid = (int)std::min<int64_t>(blocks_needed, (int64_t)ctx->sm_count * (four ? 4 : 3) * 8);
+    kern<<<grid, 128, smem, ctx->stream>>>(a);
     KLAUNCH(ctx);
     CUDA_TRY(ctx, cudaGetLastError());
     return RBFFD_OK;
+}
+
+// the straight-line monomial code of mono_row must agree with the table the other kernels (and the g rows) use
+template <int D, int Q>
+bool table_matches(const OpTables& T) {
+    static const int8_t e2[10][2] = {{0, 0}, {1, 0}, {0, 1}, {2, 0}, {1, 1}, {0, 2}, {3, 0}, {2, 1}, {1, 2}, {0, 3}};
+    static const int8_t e3[10][3] = {{0, 0, 0}, {1, 0, 0}, {0, 1, 0}, {0, 0, 1}, {2, 0, 0}, {1, 1, 0}, {1, 0, 1}, {0, 2, 0}, {0, 1, 1}, {0, 0, 2}};
+    for (int c = 0; c < Q; ++c)
+        for (int ax = 0; ax < D; ++ax)
+            if (T.mono[c][ax] != (D == 2 ? e2[c][ax] : e3[c][ax])) return false;
+    return true;
 }
 
 }  // namespace
@@ -448,7 +493,7 @@ int launch_ns(rbffd_context* ctx, const NArgs& a) {
 int rbffd_weights_ns(rbffd_context* ctx, const OpTables& T, const double* X, int64_t NS, const double* Y, int64_t M,
                      const int32_t* stencils, int32_t* colind_out, double* vals_out, int* fail_flag) {
     const int nb = T.n - T.q;
-    if (T.nops > 8 || T.n > 32 || T.q > NS_QP || nb < 1 || nb > NS_NB || T.dim < 2 || NS != M) return RBFFD_ERR_UNSUPPORTED;
+    if (T.nops > 8 || T.n > 32 || nb < 1 || nb > NS_NB || T.dim < 2 || NS != M) return RBFFD_ERR_UNSUPPORTED;
     // conditional definiteness needs polynomial degree >= (p-1)/2: q >= C((p-1)/2 + d, d)
     {
         int need = 1;
@@ -459,11 +504,30 @@ int rbffd_weights_ns(rbffd_context* ctx, const OpTables& T, const double* X, int
     NArgs a;
     a.X = X; a.Y = Y; a.stencils = stencils; a.NS = NS; a.M = M;
     a.colind = colind_out; a.vals = vals_out; a.fail = fail_flag; a.T = T;
+    // d^alpha x^e (0) = alpha! [e == alpha]
+    for (int o = 0; o < 8; ++o) { a.gzcol[o] = -1; a.gzval[o] = 0.0; }
+    for (int o = 0; o < T.nops; ++o) {
+        if (T.kind[o] != RBFFD_OP_DERIV) continue;
+        for (int c = 0; c < T.q; ++c) {
+            bool hit = true;
+            double v = 1.0;
+            for (int ax = 0; ax < T.dim; ++ax) {
+                hit = hit && T.mono[c][ax] == T.alpha[o][ax];
+                for (int u = 2; u <= T.alpha[o][ax]; ++u) v *= (double)u;
+            }
+            if (hit) { a.gzcol[o] = c; a.gzval[o] = v; }
+        }
+    }
     DevBuf<int> redo;
     CUDA_TRY(ctx, redo.alloc(1, ctx->stream));
     CUDA_TRY(ctx, cudaMemsetAsync(redo.p, 0, sizeof(int), ctx->stream));
     a.redo = redo.p;
-    int rc = T.dim == 2 ? launch_ns<2>(ctx, a) : launch_ns<3>(ctx, a);
+    int rc = RBFFD_ERR_UNSUPPORTED;
+    if (T.dim == 2 && T.q == 3 && table_matches<2, 3>(T)) rc = launch_ns<2, 3>(ctx, a);
+    else if (T.dim == 2 && T.q == 6 && table_matches<2, 6>(T)) rc = launch_ns<2, 6>(ctx, a);
+    else if (T.dim == 2 && T.q == 10 && table_matches<2, 10>(T)) rc = launch_ns<2, 10>(ctx, a);
+    else if (T.dim == 3 && T.q == 4 && table_matches<3, 4>(T)) rc = launch_ns<3, 4>(ctx, a);
+    else if (T.dim == 3 && T.q == 10 && table_matches<3, 10>(T)) rc = launch_ns<3, 10>(ctx, a);
     if (rc != RBFFD_OK) return rc;
     int h_redo = 0;
     CUDA_TRY(ctx, cudaMemcpyAsync(&h_redo, redo.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
