@@ -3,6 +3,9 @@
 #include <cstring>
 #include <new>
 
+#include <chrono>
+#include <cstdlib>
+
 #include "common.cuh"
 
 int rbffd_spmv_multi_impl(rbffd_operator* op, int nterms, const int32_t* which, const double* coef, const double* x,
@@ -96,6 +99,8 @@ int rbffd_create(int device, rbffd_context** out) {
         ctx->own_stream = true;
         for (int i = 0; i < 8 && e == cudaSuccess; ++i) e = cudaEventCreate(&ctx->ev[i]);
     }
+    if (e == cudaSuccess) e = cudaHostAlloc((void**)&ctx->hflags, 16 * sizeof(int), cudaHostAllocMapped);
+    if (e == cudaSuccess) e = cudaHostGetDevicePointer((void**)&ctx->hflags_dev, ctx->hflags, 0);
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&ctx->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
     if (e == cudaSuccess) {
@@ -122,6 +127,7 @@ int rbffd_destroy(rbffd_context* ctx) {
     for (int i = 0; i < 8; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     for (int i = 0; i < 4; ++i) if (ctx->chunk_ev[i]) cudaEventDestroy(ctx->chunk_ev[i]);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    if (ctx->hflags) cudaFreeHost(ctx->hflags);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return RBFFD_OK;
@@ -264,50 +270,59 @@ int rbffd_generate_operator_host(rbffd_context* ctx, const rbffd_options* opts, 
         CUDA_TRY(ctx, dG.alloc(N, st));
         CUDA_TRY(ctx, cudaMemcpyAsync(dG.p, xgroup, sizeof(int32_t) * N, cudaMemcpyHostToDevice, st));
     }
-    // Collocated rows with pinned output buffers: the rows are generated in chunks and every finished chunk is copied
-    // to the host on a second stream while the next chunk is being solved (the 480 MB D2H of config 2 costs more than
-    // the kernels).  Anything else takes the one-shot path.
+    // Collocated rows with pinned output buffers: the column indices are known as soon as the neighbour search is done
+    // (they ARE the stencils), so their D2H starts right away on a second stream and runs under the weight solve; the
+    // rows are solved in chunks and every finished chunk of values follows on the same copy stream while the next chunk
+    // is being solved (the 480 MB D2H of config 2 costs more than the kernels).  Anything else takes the one-shot path.
     cudaPointerAttributes pa_c, pa_v;
     const bool pinned = cudaPointerGetAttributes(&pa_c, colind_out) == cudaSuccess && pa_c.type == cudaMemoryTypeHost &&
                         cudaPointerGetAttributes(&pa_v, vals_out) == cudaSuccess && pa_v.type == cudaMemoryTypeHost;
     cudaGetLastError();
     const int nchunks = 8;
     if (pinned && Y == X && M == N && M >= 64 * nchunks && !opts->sort_columns) {
+        const bool trace = getenv("RBFFD_TRACE") != nullptr;
+        const auto t_begin = std::chrono::steady_clock::now();
+        auto lap = [&](const char* what) {
+            if (trace) fprintf(stderr, "[rbffd trace] %-28s %8.3f ms\n", what,
+                               std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count());
+        };
         for (int i = 0; i < 8; ++i) ctx->timings[i] = 0.0;
         const int nops = opts->nops;
         DevBuf<int32_t> stencils;
+        DevBuf<int64_t> c64;
         CUDA_TRY(ctx, stencils.alloc((size_t)N * n, st));
+        CUDA_TRY(ctx, c64.alloc((size_t)N * n, st));
         RBFFD_TRY(rbffd_stencils_impl(ctx, dX.p, N, dim, dX.p, N, n, xgroup ? dG.p : nullptr, stencils.p, nullptr, nullptr, nullptr));
         const int64_t ch = ((M + nchunks - 1) / nchunks + 31) / 32 * 32;
-        DevBuf<int32_t> c32[2];
-        DevBuf<int64_t> c64[2];
-        DevBuf<double> vb[2];
-        for (int b = 0; b < 2; ++b) {
-            CUDA_TRY(ctx, c32[b].alloc((size_t)ch * n, st));
-            CUDA_TRY(ctx, c64[b].alloc((size_t)ch * n, st));
-            CUDA_TRY(ctx, vb[b].alloc((size_t)ch * n * nops, st));
-        }
-        CUDA_TRY(ctx, cudaStreamSynchronize(st));
+        DevBuf<int32_t> c32;                       // the weight kernels write the pattern too; here it is the stencil array itself
+        DevBuf<double> vb;                         // every chunk has its own slice: the solve never waits for a copy
+        CUDA_TRY(ctx, c32.alloc((size_t)ch * n, st));
+        CUDA_TRY(ctx, vb.alloc((size_t)M * n * nops, st));
+        i32_to_i64_kernel<<<ceil_div_i64(N * n, 256), 256, 0, st>>>(stencils.p, N * n, opts->index_base, c64.p);
+        KLAUNCH(ctx);
+        CUDA_TRY(ctx, cudaEventRecord(ctx->chunk_ev[2], st));
+        CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->chunk_ev[2], 0));
+        CUDA_TRY(ctx, cudaMemcpyAsync(colind_out, c64.p, sizeof(int64_t) * N * n, cudaMemcpyDeviceToHost, ctx->copy_stream));
+        lap("search + colind D2H queued");
         double t_weights = 0.0;
         int rc = RBFFD_OK;
         int c = 0;
+        ctx->trusted_stencils = true;              // produced by our own search: no range check per chunk
         for (int64_t r0 = 0; r0 < M && rc == RBFFD_OK; r0 += ch, ++c) {
             const int64_t cnt = std::min<int64_t>(ch, M - r0);
-            const int b = c & 1;
-            if (c >= 2) CUDA_TRY(ctx, cudaStreamWaitEvent(st, ctx->chunk_ev[b], 0));       // buffer b is free again
-            rc = rbffd_weights_impl(ctx, opts, dX.p, N, dX.p + r0 * dim, cnt, stencils.p + r0 * n, cnt, nullptr, c32[b].p, vb[b].p);
+            double* vchunk = vb.p + (size_t)r0 * n * nops;
+            rc = rbffd_weights_impl(ctx, opts, dX.p, N, dX.p + r0 * dim, cnt, stencils.p + r0 * n, cnt, nullptr, c32.p, vchunk);
             t_weights += ctx->timings[3];
             if (rc != RBFFD_OK) break;
             // weights_impl has synchronised `st`: chunk c is complete; ship it on the copy stream
-            i32_to_i64_kernel<<<ceil_div_i64(cnt * n, 256), 256, 0, ctx->copy_stream>>>(c32[b].p, cnt * n, opts->index_base, c64[b].p);
-            KLAUNCH(ctx);
-            CUDA_TRY(ctx, cudaMemcpyAsync(colind_out + r0 * n, c64[b].p, sizeof(int64_t) * cnt * n, cudaMemcpyDeviceToHost, ctx->copy_stream));
             for (int o = 0; o < nops; ++o)
-                CUDA_TRY(ctx, cudaMemcpyAsync(vals_out + ((size_t)o * M + r0) * n, vb[b].p + (size_t)o * cnt * n, sizeof(double) * cnt * n,
+                CUDA_TRY(ctx, cudaMemcpyAsync(vals_out + ((size_t)o * M + r0) * n, vchunk + (size_t)o * cnt * n, sizeof(double) * cnt * n,
                                               cudaMemcpyDeviceToHost, ctx->copy_stream));
-            CUDA_TRY(ctx, cudaEventRecord(ctx->chunk_ev[b], ctx->copy_stream));
+            lap("chunk solved");
         }
+        ctx->trusted_stencils = false;
         cudaError_t e = cudaStreamSynchronize(ctx->copy_stream);
+        lap("copies drained");
         ctx->timings[3] = t_weights;
         // the stream-ordered temporaries are freed on `st`: make sure the copy stream is done with them first
         if (rc != RBFFD_OK) return rc;

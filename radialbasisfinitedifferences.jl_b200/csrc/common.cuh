@@ -20,6 +20,9 @@ struct rbffd_context {
     cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     int sm_count = 148;
     int max_smem_optin = 0;
+    int* hflags = nullptr;       // 16 ints of mapped pinned host memory: status words are published with plain stores from a
+    int* hflags_dev = nullptr;   // tiny kernel, never by a D2H memcpy (that would queue behind bulk D2H traffic on the copy engine)
+    bool trusted_stencils = false;   // set by internal callers whose stencils come from our own search (skips range checks)
     long long launches = 0;      // hand-written kernels launched through this context (rbffd_launch_count)
 };
 
@@ -76,6 +79,24 @@ struct DevBuf {
 };
 
 static inline int ceil_div_i64(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+#ifdef __CUDACC__
+static __global__ void rbffd_publish_kernel(const int* __restrict__ src, int n, volatile int* dst) {
+    if ((int)threadIdx.x < n) dst[threadIdx.x] = src[threadIdx.x];
+    __threadfence_system();
+}
+static __global__ void rbffd_set_flags_kernel(int* dst, int v0, int v1, int v2, int v3) {
+    if (threadIdx.x == 0) { dst[0] = v0; dst[1] = v1; dst[2] = v2; dst[3] = v3; }
+}
+// device status words -> host, through mapped pinned memory (n <= 16); synchronises the context's stream
+static inline cudaError_t rbffd_fetch_flags(rbffd_context* ctx, const int* dev, int n, int* out) {
+    rbffd_publish_kernel<<<1, 32, 0, ctx->stream>>>(dev, n, ctx->hflags_dev);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e == cudaSuccess) for (int i = 0; i < n; ++i) out[i] = ((volatile int*)ctx->hflags)[i];
+    return e;
+}
+#endif
 
 // ---- internal entry points shared between translation units ----------------------------------------
 struct KnnGridPlan;   // knn.cu

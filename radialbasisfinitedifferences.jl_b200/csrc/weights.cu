@@ -427,23 +427,23 @@ int rbffd_weights_impl(rbffd_context* ctx, const rbffd_options* opts, const doub
     if (!Y) Y = X;
 
     DevBuf<int> flags;   // [0] singular node+1, [1] centre != identity, [2] bad index
-    CUDA_TRY(ctx, flags.alloc(3, st));
-    int h_flags[3] = {0x7fffffff, 0, 0};
-    CUDA_TRY(ctx, cudaMemcpyAsync(flags.p, h_flags, sizeof(h_flags), cudaMemcpyHostToDevice, st));
-    check_range_kernel<<<ceil_div_i64(N * T.n, 256), 256, 0, st>>>(stencils, N * T.n, (int)NX, flags.p + 2);
-    KLAUNCH(ctx);
+    CUDA_TRY(ctx, flags.alloc(4, st));
+    int h_flags[4] = {0x7fffffff, 0, 0, 0};
+    rbffd_set_flags_kernel<<<1, 32, 0, st>>>(flags.p, h_flags[0], h_flags[1], h_flags[2], h_flags[3]);
+    if (!ctx->trusted_stencils) {
+        check_range_kernel<<<ceil_div_i64(N * T.n, 256), 256, 0, st>>>(stencils, N * T.n, (int)NX, flags.p + 2);
+        KLAUNCH(ctx);
+    }
     bool identity = false;
     if (center) {
         check_range_kernel<<<ceil_div_i64(M, 256), 256, 0, st>>>(center, M, (int)N, flags.p + 2);
         KLAUNCH(ctx);
         if (M == N) { check_identity_kernel<<<ceil_div_i64(M, 256), 256, 0, st>>>(center, M, flags.p + 1); KLAUNCH(ctx); }
-        CUDA_TRY(ctx, cudaMemcpyAsync(h_flags, flags.p, sizeof(h_flags), cudaMemcpyDeviceToHost, st));
-        CUDA_TRY(ctx, cudaStreamSynchronize(st));
+        CUDA_TRY(ctx, rbffd_fetch_flags(ctx, flags.p, 4, h_flags));
         identity = (M == N) && h_flags[1] == 0;
     } else {
         if (M != N) RBFFD_FAIL(ctx, RBFFD_ERR_INVALID, "center == NULL requires M == N");
-        CUDA_TRY(ctx, cudaMemcpyAsync(h_flags, flags.p, sizeof(h_flags), cudaMemcpyDeviceToHost, st));
-        CUDA_TRY(ctx, cudaStreamSynchronize(st));
+        if (!ctx->trusted_stencils) CUDA_TRY(ctx, rbffd_fetch_flags(ctx, flags.p, 4, h_flags));
         identity = true;
     }
     if (h_flags[2]) RBFFD_FAIL(ctx, RBFFD_ERR_INVALID, "stencil or centre index out of range");
@@ -514,8 +514,7 @@ int rbffd_weights_impl(rbffd_context* ctx, const rbffd_options* opts, const doub
         CUDA_TRY(ctx, cudaGetLastError());
     }
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev[6], st));
-    CUDA_TRY(ctx, cudaMemcpyAsync(h_flags, flags.p, sizeof(h_flags), cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(ctx, cudaStreamSynchronize(st));
+    CUDA_TRY(ctx, rbffd_fetch_flags(ctx, flags.p, 4, h_flags));
     float ms;
     CUDA_TRY(ctx, cudaEventElapsedTime(&ms, ctx->ev[4], ctx->ev[5]));
     ctx->timings[3] = ms;

@@ -61,6 +61,15 @@ __device__ __forceinline__ double fast_rsqrt(double x) {
     return fma(y, u, y);
 }
 
+// 1/x to ~1 ulp: MUFU.RCP64H seed (relative error ~2^-20) + one third-order step y (1 + e + e^2), e = 1 - x y
+__device__ __forceinline__ double rcp3(double x) {
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double e = fma(-x, y, 1.0);
+    const double u = fma(e, e, e);
+    return fma(y, u, y);
+}
+
 // max over the warp of a non-negative double: ordering of non-negative doubles == ordering of their bit patterns
 __device__ __forceinline__ double warp_max_nonneg(double v) {
     const unsigned hi = (unsigned)__double2hiint(v), lo = (unsigned)__double2loint(v);
@@ -92,7 +101,7 @@ __host__ __device__ constexpr int lap_col(int a) {
     return D == 2 ? (Q > 3 ? (a == 0 ? 3 : 5) : -1) : (Q > 4 ? (a == 0 ? 4 : (a == 1 ? 7 : 9)) : -1);
 }
 
-template <int D, int Q, int MINB>
+template <int D, int Q, int MINB, bool FOLD>
 __global__ void __launch_bounds__(128, MINB) weights_ns_kernel(NArgs a) {
     constexpr int LD = NS_LD, US = NS_US;
     constexpr int KS = (Q + 3) / 4, QP = 4 * KS;      // k-steps of the DMMAs over the basic nodes
@@ -106,17 +115,19 @@ __global__ void __launch_bounds__(128, MINB) weights_ns_kernel(NArgs a) {
     double* Wt = G + 32 * US;                         // [32][QP]: W' rows of the non-basic nodes, then the w_p rows
     double* Bt = Wt + 32 * QP;                        // [32][BS]: RBF right-hand sides by position
     double* Ys = Bt;                                  // solution y, [op][24] (Bt is dead by then)
-    double* Sc = Bt + 32 * BS;                        // permuted scaled coordinates
-    int* perm = reinterpret_cast<int*>(Sc + 32 * D);
+    constexpr int DP = D == 2 ? 2 : 4;                // doubles per stored point (16-byte aligned)
+    double* Sc = Bt + 32 * BS;                        // permuted scaled coordinates, [pos][DP]
+    int* perm = reinterpret_cast<int*>(Sc + 32 * DP);
     const double EPS = 2.220446049250313e-16;
     const unsigned FULL = 0xffffffffu;
     const double sgn = (((T.p + 1) >> 1) & 1) ? -1.0 : 1.0;       // (-1)^((p+1)/2) S is positive definite
     const int hp = (T.p - 1) >> 1;
+    const int sgnbits = sgn < 0.0 ? (int)0x80000000 : 0;
     // right-hand-side columns: in the spare columns of the last null-space tile when they fit, else in a 4th tile column
     const int rc0 = (nb + 3) & ~3;
-    const bool fold = rc0 + nops <= NS_NB;
+    constexpr bool fold = FOLD;                       // host: rc0 + nops <= NS_NB
     const int rcb = fold ? rc0 : NS_NB;               // first right-hand-side column; also the row of w_p in Wt
-    const int NJ = fold ? 3 : 4;
+    constexpr int NJ = fold ? 3 : 4;
     const bool gl = n + nops <= 32;                   // g rows fit into spare lanes of the column reduction
     const int go = gl ? lane - n : lane;              // operator whose g row this lane owns
     const bool gown = go >= 0 && go < nops;
@@ -177,7 +188,8 @@ __global__ void __launch_bounds__(128, MINB) weights_ns_kernel(NArgs a) {
                 else grow[c] = gown ? gv[c] : 0.0;
             }
         }
-        bool ok = true;
+        unsigned kmin = 0xffffffffu;
+        int bad = 0;                                            // sign bit set: a pivot of S had the wrong sign
         bool basic = false;
         int mybasic = 0;
 #pragma unroll
@@ -185,13 +197,14 @@ __global__ void __launch_bounds__(128, MINB) weights_ns_kernel(NArgs a) {
             const unsigned hi = (unsigned)__double2hiint(prow[j]) & 0x7fffffe0u;
             const unsigned key = (lane < n && !basic) ? (hi | (unsigned)lane) : 0u;
             const unsigned kmax = __reduce_max_sync(FULL, key);
-            ok = ok && kmax >= 32u;                             // P is rank deficient on this stencil otherwise
+            const double rown = rcp3(prow[j]);                  // every candidate inverts its own entry under the search
+            kmin = min(kmin, kmax);                             // < 32: P is rank deficient on this stencil
             const int pl = kmax & 31;
             if (lane == pl) { basic = true; mybasic = j; }
             double pr[Q];
 #pragma unroll
-            for (int c = 0; c < Q; ++c) pr[c] = __shfl_sync(FULL, prow[c], pl);
-            const double rinv = fast_rcp(pr[j]);
+            for (int c = 0; c < Q; ++c) pr[c] = c == j ? 0.0 : __shfl_sync(FULL, prow[c], pl);
+            const double rinv = __shfl_sync(FULL, rown, pl);
             const double tl = prow[j] * rinv;
 #pragma unroll
             for (int c = 0; c < Q; ++c)
@@ -234,7 +247,7 @@ __global__ void __launch_bounds__(128, MINB) weights_ns_kernel(NArgs a) {
             perm[pos] = lane;
             G[pos * LD + pos] = 0.0;
 #pragma unroll
-            for (int c = 0; c < D; ++c) Sc[pos * D + c] = sx[c];
+            for (int c = 0; c < D; ++c) Sc[pos * DP + c] = sx[c];
             // RBF part of the right-hand sides at this node (generate_operator.jl:123-154)
             double del[D];
             double r2 = 0.0;
@@ -252,25 +265,46 @@ __global__ void __launch_bounds__(128, MINB) weights_ns_kernel(NArgs a) {
         }
         __syncwarp();
         // ---- 3. Phi~ in permuted order, by symmetric pairs ----
-        // iteration tt pairs row tt with columns tt+1.. (lanes < n-1-tt) and row n-1-tt with columns lane+1 (the
-        // other lanes): every iteration fills n-1 entries
+        // lane l owns position l; in round k it pairs with position (l + k) mod n.  Rounds 1 .. n/2 visit every
+        // unordered pair (the last round of an even n visits its pairs twice, with identical values).  Coincident
+        // nodes give r2 = 0 -> NaN, which the finiteness check of the weights turns into the pivoted fallback.
         {
-            const int half = (n + 1) >> 1;
-            for (int tt = 0; tt < half; ++tt) {
-                const int i2 = n - 1 - tt;
-                const bool first = lane < i2;
-                const int ia = first ? tt : i2;
-                const int ib = first ? tt + 1 + lane : lane + 1;
-                if (lane < n - 1 && (first || i2 != tt)) {
-                    double r2 = 0.0;
+            double me[D];
+            const int l = lane < n ? lane : 0;
 #pragma unroll
-                    for (int c = 0; c < D; ++c) { const double dd = Sc[ia * D + c] - Sc[ib * D + c]; r2 = fma(dd, dd, r2); }
-                    double v = fast_rsqrt(r2);
-                    for (int e = 0; e <= hp; ++e) v *= r2;      // r^p = r2^((p+1)/2) / r
-                    v = r2 > 0.0 ? v : 0.0;
-                    G[ia * LD + ib] = v;
-                    G[ib * LD + ia] = v;
+            for (int c = 0; c < D; ++c) me[c] = Sc[l * DP + c];
+            double* const grow_l = G + l * LD;
+            double* const gcol_l = G + l;
+            const int rounds = n >> 1;
+            auto phi = [&](int k, int& ib) -> double {
+                ib = l + k;
+                ib = ib >= n ? ib - n : ib;
+                double o[D];
+                if constexpr (D == 2) {
+                    const double2 v = *reinterpret_cast<const double2*>(Sc + ib * DP);
+                    o[0] = v.x; o[1] = v.y;
+                } else {
+                    const double2 v = *reinterpret_cast<const double2*>(Sc + ib * DP);
+                    o[0] = v.x; o[1] = v.y; o[2] = Sc[ib * DP + 2];
                 }
+                double r2 = 0.0;
+#pragma unroll
+                for (int c = 0; c < D; ++c) { const double dd = me[c] - o[c]; r2 = fma(dd, dd, r2); }
+                double v = fast_rsqrt(r2);
+                for (int e = 0; e <= hp; ++e) v *= r2;          // r^p = r2^((p+1)/2) / r
+                return v;
+            };
+            int k = 1;
+            for (; k + 1 <= rounds; k += 2) {                   // two independent dependency chains per trip
+                int b0, b1;
+                const double v0 = phi(k, b0);
+                const double v1 = phi(k + 1, b1);
+                if (lane < n) { grow_l[b0] = v0; gcol_l[b0 * LD] = v0; grow_l[b1] = v1; gcol_l[b1 * LD] = v1; }
+            }
+            if (k <= rounds) {
+                int b0;
+                const double v0 = phi(k, b0);
+                if (lane < n) { grow_l[b0] = v0; gcol_l[b0 * LD] = v0; }
             }
         }
         __syncwarp();
@@ -330,19 +364,23 @@ __global__ void __launch_bounds__(128, MINB) weights_ns_kernel(NArgs a) {
                 }
         }
         __syncwarp();
-        // identity padding outside the nb x nb block; right-hand-side columns of padded rows are zero
+        // identity padding outside the nb x nb block; right-hand-side columns of padded rows are zero.  Only tiles that
+        // reach past row / column nb are touched (warp-uniform tests).
 #pragma unroll
         for (int I = 0; I < 3; ++I) {
             const int row = 8 * I + g;
 #pragma unroll
-            for (int J = 0; J < 3; ++J)
+            for (int J = 0; J < 3; ++J) {
+                if (8 * I + 8 > nb || 8 * J + 8 > nb) {
 #pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                    const int col = 8 * J + 2 * t + e;
-                    if (col >= rcb) { if (row >= nb) c[I][J][e] = 0.0; }
-                    else if (row >= nb || col >= nb) c[I][J][e] = row == col ? sgn : 0.0;
+                    for (int e = 0; e < 2; ++e) {
+                        const int col = 8 * J + 2 * t + e;
+                        if (col >= rcb) { if (row >= nb) c[I][J][e] = 0.0; }
+                        else if (row >= nb || col >= nb) c[I][J][e] = row == col ? sgn : 0.0;
+                    }
                 }
-            if (row >= nb) { c[I][3][0] = 0.0; c[I][3][1] = 0.0; }
+            }
+            if (!fold && row >= nb) { c[I][3][0] = 0.0; c[I][3][1] = 0.0; }
         }
         // ---- 6. blocked Gauss-Jordan WITHOUT pivoting on the definite S: the block step of weights_fast.cu with
         //         static pivot rows (row 4kb+s), so no pivot search, no row selects and a static pivot-row dump ----
@@ -377,8 +415,8 @@ __global__ void __launch_bounds__(128, MINB) weights_ns_kernel(NArgs a) {
                     for (int cc = sidx; cc < 4; ++cc) pv[cc] = __shfl_sync(FULL, av[cc], pr);
 #pragma unroll
                     for (int cc = 0; cc < sidx; ++cc) wp[cc] = __shfl_sync(FULL, w[cc], pr);
-                    ok = ok && (sgn * pv[sidx] > 0.0);    // S not definite: the pivoted kernel must take over
-                    const double rinv = fast_rcp(pv[sidx]);
+                    bad |= __double2hiint(pv[sidx]) ^ sgnbits;    // S not definite: the pivoted kernel must take over
+                    const double rinv = rcp3(pv[sidx]);
                     if (lane == 0) rinv_s[pr] = rinv;
                     const double nl = lane == pr ? 0.0 : av[sidx] * (-rinv);
 #pragma unroll
@@ -430,6 +468,7 @@ __global__ void __launch_bounds__(128, MINB) weights_ns_kernel(NArgs a) {
         __syncwarp();
         // ---- 7. w[N] = y, w[B] = w_p - W y; rescale and scatter into the CSR row (generate_operator.jl:161-182) ----
         const int dstj = perm[lane < n ? lane : 0];
+        bool ok = kmin >= 32u && bad >= 0;
         for (int o = 0; o < nops; ++o) {
             const double f = op_post_factor<D>(T, o, s);
             double* vrow = a.vals + ((int64_t)o * a.M + i) * n;
@@ -448,7 +487,10 @@ __global__ void __launch_bounds__(128, MINB) weights_ns_kernel(NArgs a) {
                 if (aa < nb) acc0 = fma(-wcol[aa * QP], yv[aa], acc0);
                 wv = acc0 + acc1;
             }
-            if (lane < n) vrow[dstj] = ok ? f * wv : nan("");
+            wv *= f;
+            // a zero pivot shows up as a non-finite weight
+            ok = ok && __all_sync(FULL, fabs(wv) < __longlong_as_double(0x7ff0000000000000ll));
+            if (lane < n) vrow[dstj] = ok ? wv : nan("");
         }
         if (lane < n) a.colind[i * n + lane] = id;
         if (!ok && lane == 0) *a.redo = 1;
@@ -460,12 +502,15 @@ template <int D, int Q>
 int launch_ns(rbffd_context* ctx, NArgs& a) {
     constexpr int QP = 4 * ((Q + 3) / 4);
     a.bs = (a.T.nops + 1) & ~1;
-    a.smem_per_warp = ((32 * NS_US + 32 * QP + 32 * a.bs + 32 * D) * 8 + 32 * 4 + 15) & ~15;
+    a.smem_per_warp = ((32 * NS_US + 32 * QP + 32 * a.bs + 32 * (D == 2 ? 2 : 4)) * 8 + 32 * 4 + 15) & ~15;
     const size_t smem = (size_t)a.smem_per_warp * 4;
     if ((int64_t)smem > ctx->max_smem_optin) return RBFFD_ERR_UNSUPPORTED;
     // 4 CTAs (16 warps) per SM when the shared-memory tile allows it, else 3
     const bool four = (smem + 1024) * 4 <= 228 * 1024;
-    auto kern = four ? weights_ns_kernel<D, Q, 4> : weights_ns_kernel<D, Q, 3>;
+    const int nb = a.T.n - Q;
+    const bool fold = ((nb + 3) & ~3) + a.T.nops <= NS_NB;
+    auto kern = four ? (fold ? weights_ns_kernel<D, Q, 4, true> : weights_ns_kernel<D, Q, 4, false>)
+                     : (fold ? weights_ns_kernel<D, Q, 3, true> : weights_ns_kernel<D, Q, 3, false>);
     CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t blocks_needed = (a.NS + 3) / 4;
     const int grid = (int)std::min<int64_t>(blocks_needed, (int64_t)ctx->sm_count * (four ? 4 : 3) * 8);
@@ -530,7 +575,6 @@ int rbffd_weights_ns(rbffd_context* ctx, const OpTables& T, const double* X, int
     else if (T.dim == 3 && T.q == 10 && table_matches<3, 10>(T)) rc = launch_ns<3, 10>(ctx, a);
     if (rc != RBFFD_OK) return rc;
     int h_redo = 0;
-    CUDA_TRY(ctx, cudaMemcpyAsync(&h_redo, redo.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    CUDA_TRY(ctx, rbffd_fetch_flags(ctx, redo.p, 1, &h_redo));
     return h_redo ? RBFFD_ERR_UNSUPPORTED : RBFFD_OK;
 }
