@@ -154,6 +154,22 @@ def test_nullspace_kernel_vs_oracle(ctx, oracle, d, g, p, deg, n, ops):
     _check_weights(v3, rvals, cond, ops)
 
 
+@pytest.mark.parametrize("d,g,p,deg,n,ops", [
+    (2, 36, 5, 5, 42, ["E", "Dx", "Dy", "Dxx", "Dyy", "Dxy", ("Dk", 0, 4), ("Dk", 1, 4)]),   # config 1 (adv_diff_test.jl): q=21, nb=21
+    (2, 36, 5, 4, 50, ["Dxx", "Dyy", ("Dk", 0, 4), ("Dk", 1, 4)]),                     # config 3: q=15, nb=35
+    (3, 14, 7, 3, 60, ["Lap", "Dx", "Dy", "Dz"]),                                       # configs 4/5: q=20, nb=40
+    (2, 30, 5, 4, 62, ["Lap", "Dx"]),                                                   # nb=47: right-hand sides in a 7th tile column
+    (2, 30, 5, 3, 46, ["Lap", "Dx"]), (3, 12, 5, 2, 40, ["Lap", "Dz"]),                 # q=10 with n > 32
+    (3, 12, 7, 3, 33, ["E", "Dx", "Dy", "Dz", "Dxx", "Dyy", "Dzz", "Dxy"])])            # small null space (nb=13), 8 operators
+def test_multiwarp_nullspace_kernel_vs_oracle(ctx, oracle, d, g, p, deg, n, ops):
+    """kernel=3 with n > 32 runs the multi-warp null-space kernel (weights_nsw.cu).  Same tolerance as every other kernel."""
+    X = rb.nodes.jittered_lattice(d, g, seed=8)
+    c3, v3 = rb.generate_raw(X, None, p, n, deg, ops, ctx=ctx, kernel=3)
+    rcol, rvals, cond = oracle.generate_operator(X, X, p, n, deg, ops=ops, mode=0, want_cond=True)
+    assert np.array_equal(c3, rcol)
+    _check_weights(v3, rvals, cond, ops)
+
+
 def test_nullspace_kernel_falls_back_when_not_definite(ctx, oracle):
     """polydeg < (p-1)/2: Z'Phi Z is not definite, kernel=3 refuses and the automatic dispatch uses the pivoted kernels."""
     X = rb.nodes.jittered_lattice(2, 30, seed=8)
