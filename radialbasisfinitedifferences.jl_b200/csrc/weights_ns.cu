@@ -70,6 +70,19 @@ __device__ __forceinline__ double rcp3(double x) {
     return fma(y, u, y);
 }
 
+// r^p = r2^((p+1)/2) / r for odd p, hp = (p-1)/2; straight-line for p = 3, 5, 7, 9 (warp-uniform selects)
+__device__ __forceinline__ double phs_pow(double r2, double y, int hp) {
+    if (hp == 0) return r2 * y;                         // p = 1
+    const double r4 = r2 * r2;
+    double v = r4 * y;                                  // r^3
+    if (hp <= 4) {
+        const double m = (hp & 1) ? 1.0 : r2;           // p = 5, 9: one more r2
+        const double q4 = hp >= 3 ? r4 : 1.0;           // p = 7, 9: one more r^4
+        return hp == 1 ? v : v * (m * q4);
+    }
+    for (int e = 1; e < hp; ++e) v *= r2;
+    return v;
+}
 // max over the warp of a non-negative double: ordering of non-negative doubles == ordering of their bit patterns
 __device__ __forceinline__ double warp_max_nonneg(double v) {
     const unsigned hi = (unsigned)__double2hiint(v), lo = (unsigned)__double2loint(v);
@@ -290,9 +303,7 @@ __global__ void __launch_bounds__(128, MINB) weights_ns_kernel(NArgs a) {
                 double r2 = 0.0;
 #pragma unroll
                 for (int c = 0; c < D; ++c) { const double dd = me[c] - o[c]; r2 = fma(dd, dd, r2); }
-                double v = fast_rsqrt(r2);
-                for (int e = 0; e <= hp; ++e) v *= r2;          // r^p = r2^((p+1)/2) / r
-                return v;
+                return phs_pow(r2, fast_rsqrt(r2), hp);
             };
             int k = 1;
             for (; k + 1 <= rounds; k += 2) {                   // two independent dependency chains per trip

@@ -60,6 +60,19 @@ __device__ __forceinline__ double rcp3w(double x) {
     const double u = fma(e, e, e);
     return fma(y, u, y);
 }
+// r^p = r2^((p+1)/2) / r for odd p, hp = (p-1)/2; straight-line for p = 3, 5, 7, 9 (warp-uniform selects)
+__device__ __forceinline__ double phs_pow(double r2, double y, int hp) {
+    if (hp == 0) return r2 * y;                         // p = 1
+    const double r4 = r2 * r2;
+    double v = r4 * y;                                  // r^3
+    if (hp <= 4) {
+        const double m = (hp & 1) ? 1.0 : r2;           // p = 5, 9: one more r2
+        const double q4 = hp >= 3 ? r4 : 1.0;           // p = 7, 9: one more r^4
+        return hp == 1 ? v : v * (m * q4);
+    }
+    for (int e = 1; e < hp; ++e) v *= r2;
+    return v;
+}
 __device__ __forceinline__ double warp_max_nn(double v) {
     const unsigned hi = (unsigned)__double2hiint(v), lo = (unsigned)__double2loint(v);
     const unsigned hmax = __reduce_max_sync(0xffffffffu, hi);
@@ -299,9 +312,7 @@ __global__ void __launch_bounds__(128, 4) weights_nsw_kernel(WNArgs a) {
                 double r2 = 0.0;
 #pragma unroll
                 for (int c = 0; c < D; ++c) { const double dd = sx[c] - o[c]; r2 = fma(dd, dd, r2); }
-                double vv = rsqrt3(r2);
-                for (int e = 0; e <= hp; ++e) vv *= r2;         // r^p = r2^((p+1)/2) / r
-                return vv;
+                return phs_pow(r2, rsqrt3(r2), hp);
             };
             int k = 1;
             for (; k + 1 <= rounds; k += 2) {
