@@ -59,7 +59,11 @@ typedef struct {
     int32_t sort_columns; /* != 0: entries of every row sorted by column (CSR form of the CSC the reference builds) */
     int32_t kernel;     /* 0 = auto, 1 = generic shared-memory LU kernel, 2 = register/DMMA Gauss-Jordan kernels,
                            3 = null-space kernel (2 and 3: error if not applicable) */
-    int32_t reserved[5];
+    int32_t variant;    /* 0 = scaled two-set methods (generate_operator.jl:29,192; hyperviscosity_operator.jl:26,177)
+                           1 = legacy collocated methods generate_operator(X, p, n, polydeg) (generate_operator.jl:354) and
+                               hyperviscosity_operator(K, X, p, n, polydeg) (hyperviscosity_operator.jl:314): no scaling,
+                               centre node moved to (eps, eps), RBF right-hand sides evaluated at X_j - x_c.  Y must be X. */
+    int32_t reserved[4];
 } rbffd_options;
 
 typedef struct rbffd_context rbffd_context;     /* one per (device, stream); not thread-safe, thread-compatible */

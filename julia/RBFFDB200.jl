@@ -19,16 +19,16 @@ const MAX_OPS = 12
 struct Options            # mirrors rbffd_options (include/rbffd.h)
     dim::Int32; p::Int32; polydeg::Int32; n::Int32; nops::Int32
     ops::NTuple{48,Int32}
-    index_base::Int32; sort_columns::Int32; kernel::Int32
-    reserved::NTuple{5,Int32}
+    index_base::Int32; sort_columns::Int32; kernel::Int32; variant::Int32
+    reserved::NTuple{4,Int32}
 end
 
-function make_options(dim, p, polydeg, n, ops::Vector{NTuple{4,Int}})
+function make_options(dim, p, polydeg, n, ops::Vector{NTuple{4,Int}}; variant = 0)
     flat = zeros(Int32, 4 * MAX_OPS)
     for (i, o) in enumerate(ops), j in 1:4
         flat[4 * (i - 1) + j] = o[j]
     end
-    Options(dim, p, polydeg, n, length(ops), Tuple(flat), 1, 0, 0, (0, 0, 0, 0, 0))   # index_base = 1: Julia
+    Options(dim, p, polydeg, n, length(ops), Tuple(flat), 1, 0, 0, variant, (0, 0, 0, 0))   # index_base = 1: Julia
 end
 
 const CTX = Ref{Ptr{Cvoid}}(C_NULL)
@@ -52,10 +52,10 @@ end
 # Vector{SVector{2,Float64}} is already the interleaved layout the C ABI wants: pointer(X) is a Ptr{Float64} of length 2N
 coords(X) = (Xc = convert(Vector{SVector{2,Float64}}, X); (Xc, Ptr{Float64}(pointer(Xc))))
 
-function generate(X, Y, p, n, polydeg, ops, grp)
-    Xc, px = coords(X); Yc, py = coords(Y)
+function generate(X, Y, p, n, polydeg, ops, grp; variant = 0)
+    Xc, px = coords(X); Yc, py = Y === nothing ? (Xc, Ptr{Float64}(C_NULL)) : coords(Y)
     N, M = length(Xc), length(Yc)
-    opts = Ref(make_options(2, p, polydeg, n, ops))
+    opts = Ref(make_options(2, p, polydeg, n, ops; variant = variant))
     colind = Matrix{Int64}(undef, n, M)                 # row-major [M][n] in C == column-major (n, M) in Julia
     vals = Array{Float64,3}(undef, n, M, length(ops))
     GC.@preserve Xc Yc colind vals grp begin
@@ -78,6 +78,17 @@ end
 function generate_operator(X, Y, p, n, polydeg, X_idx_in, X_idx_bc, X_idx_bc_g, Y_idx_in, Y_idx_bc, Y_idx_bc_g)
     m = generate(X, Y, p, n, polydeg, vcat([(0, 0, 0, 0)], REF_OPS), groups(length(X), X_idx_in, X_idx_bc, X_idx_bc_g))
     return m[1], m[2], m[3], m[4], m[5], m[6]
+end
+
+"legacy collocated method generate_operator(X, p, n, polydeg)   (src/generate_operator.jl:354): variant = 1"
+function generate_operator(X, p, n, polydeg)
+    m = generate(X, nothing, p, n, polydeg, vcat([(0, 0, 0, 0)], REF_OPS), nothing; variant = 1)
+    return m[1], m[2], m[3], m[4], m[5], m[6]
+end
+"legacy collocated method hyperviscosity_operator(k_deriv, X, p, n, polydeg)   (src/hyperviscosity_operator.jl:314)"
+function hyperviscosity_operator(k_deriv, X, p, n, polydeg)
+    m = generate(X, nothing, p, n, polydeg, [(0, k_deriv, 0, 0), (0, 0, k_deriv, 0)], nothing; variant = 1)
+    return m[1], m[2]
 end
 
 "hyperviscosity_operator(k_deriv, X, Y, p, n, polydeg[, index sets]) -> Dxk, Dyk   (src/hyperviscosity_operator.jl:26,177)"

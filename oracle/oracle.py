@@ -170,6 +170,17 @@ def generate_operator(X, Y, p, n, polydeg, groups=None, ops=("E", "Dx", "Dy", "D
     return colind, res
 
 
+def generate_operator_collocated(X, p, n, polydeg, ops=("E", "Dx", "Dy", "Dxx", "Dyy", "Dxy"), mode=0, want_cond=False):
+    """src/generate_operator.jl:354-491 / src/hyperviscosity_operator.jl:314-440: the legacy 4-argument methods."""
+    X = np.ascontiguousarray(X, np.float64)
+    idx, _ = knn(X, X, n)
+    center = np.arange(len(X), dtype=np.int64)
+    res = weights(X, X, idx, center, p, n, polydeg, op_table(X.shape[1], ops), mode, 1, want_cond)
+    if want_cond:
+        return idx, res[0], res[1]
+    return idx, res
+
+
 def hyperviscosity_operator(K, X, Y, p, n, polydeg, groups=None, mode=0, brute=False):
     """src/hyperviscosity_operator.jl:26-175: (Dxk, Dyk[, Dzk]) = d^K/dx_a^K per axis."""
     d = np.asarray(X).shape[1]

@@ -465,8 +465,9 @@ static int lu_solve_ld(const double* A, int m, double* b, int nrhs) {
  * mode: 0 = literal reference arithmetic  W = inv(A) * RHS   (generate_operator.jl:158)
  *       1 = LU solve in double, 2 = LU solve in long double.
  * variant: 0 = scaled two-set method (generate_operator.jl:29-190)
- *          1 = legacy collocated method (generate_operator.jl:354-491): no scaling, centre offset (eps,eps),
- *              RBF rows evaluated at X_j - x_c (odd derivatives change sign).
+ *          1 = legacy collocated method (generate_operator.jl:354-491, hyperviscosity_operator.jl:314-440): no
+ *              scaling, the centre node becomes (eps,eps) in A and in both right-hand-side blocks, RBF rows are
+ *              evaluated at X_shift[j] = X_j - x_c (:433), so odd derivatives change sign; weights not rescaled.
  * vals[nops][M][n] (row-major), cond1[N] (1-norm condition number of A_i; NULL to skip; needs mode 0).
  * returns 0, or 1+node index of the first singular stencil.
  */
@@ -525,6 +526,8 @@ int orc_weights(const double* X, int64_t N, int d, const double* Y, int64_t M,
             const double* xc = X + st[0] * d;
             /* scalestencil.jl:10-20 */
             for (int j = 0; j < n; ++j) for (int a = 0; a < d; ++a) S[j * d + a] = X[st[j] * d + a] - xc[a];
+            /* legacy collocated method: no scaling, centre node replaced by (eps, eps)  generate_operator.jl:403-410 */
+            if (variant != 0) for (int a = 0; a < d; ++a) S[a] = EPS;
             if (variant == 0) {
                 for (int a = 0; a < d; ++a) {
                     double mx = 0.0;
@@ -577,7 +580,7 @@ int orc_weights(const double* X, int64_t N, int d, const double* Y, int64_t M,
                         double del[3];
                         for (int a = 0; a < d; ++a) {
                             /* :125-133 (two-set: eta - S_j, 0 -> eps) ; :433 (legacy: S_j - centre) */
-                            double t = variant == 0 ? eta[a] - S[j * d + a] : S[j * d + a] - eta[a];
+                            double t = variant == 0 ? eta[a] - S[j * d + a] : S[j * d + a];
                             if (variant == 0 && t == 0.0) t = EPS;
                             del[a] = t;
                         }
@@ -593,7 +596,7 @@ int orc_weights(const double* X, int64_t N, int d, const double* Y, int64_t M,
                     }
                     /* polylinearoperator.jl:36-44: polynomial rows at the scaled evaluation point */
                     double pe[3];
-                    for (int a = 0; a < d; ++a) pe[a] = variant == 0 ? eta[a] : 0.0;
+                    for (int a = 0; a < d; ++a) pe[a] = eta[a];   /* legacy: polylinearoperator([X_shift[1]], ...) = (eps, eps)  :429 */
                     for (int t = 0; t < q; ++t) {
                         double v;
                         if (op[0] == ORC_OP_DERIV) v = eval_mono_deriv(ex + 3 * t, op + 1, pe, d);

@@ -4,6 +4,7 @@ The directory name is not an importable identifier; load it through the repo-roo
 """
 from ._lib import AdvDiffParams, Options, RbffdError, build, exported_symbols, lib  # noqa: F401
 from .api import (BoundaryConditions, Context, Operator, REFERENCE_OPS, calculateneighbors, default_context, generate_operator,  # noqa: F401
-                  generate_raw, groups_from_index_sets, hyperviscosity_operator, make_options)
+                  generate_operator_collocated, generate_raw, groups_from_index_sets, hyperviscosity_operator,
+                  hyperviscosity_operator_collocated, make_options)
 from . import nodes  # noqa: F401
 from .sharding import PeerHalo, SlabShard, boundary_row_ranges, exchange_halo  # noqa: F401

@@ -26,7 +26,7 @@ class RbffdError(RuntimeError):
 class Options(C.Structure):
     _fields_ = [("dim", C.c_int32), ("p", C.c_int32), ("polydeg", C.c_int32), ("n", C.c_int32), ("nops", C.c_int32),
                 ("ops", (C.c_int32 * 4) * MAX_OPS), ("index_base", C.c_int32), ("sort_columns", C.c_int32),
-                ("kernel", C.c_int32), ("reserved", C.c_int32 * 5)]
+                ("kernel", C.c_int32), ("variant", C.c_int32), ("reserved", C.c_int32 * 4)]
 
 
 class Halo(C.Structure):

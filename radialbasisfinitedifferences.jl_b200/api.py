@@ -58,7 +58,7 @@ def make_ops(dim, ops):
     return rows
 
 
-def make_options(dim, p, n, polydeg, ops, index_base=0, sort_columns=False, kernel=0):
+def make_options(dim, p, n, polydeg, ops, index_base=0, sort_columns=False, kernel=0, variant=0):
     rows = make_ops(dim, ops)
     if not 1 <= len(rows) <= _lib.MAX_OPS:
         raise ValueError(f"between 1 and {_lib.MAX_OPS} operators per call")
@@ -68,6 +68,7 @@ def make_options(dim, p, n, polydeg, ops, index_base=0, sort_columns=False, kern
         for j in range(4):
             o.ops[i][j] = r[j]
     o.index_base, o.sort_columns, o.kernel = int(index_base), int(bool(sort_columns)), int(kernel)
+    o.variant = int(variant)
     return o
 
 
@@ -306,7 +307,7 @@ def _to_csc(colind, vals, shape_mode, N):
     return [sp.csr_matrix((v.ravel(), colind.ravel(), indptr), shape=(M, ncols)).tocsc() for v in vals]
 
 
-def generate_raw(X, Y, p, n, polydeg, ops=REFERENCE_OPS, groups=None, ctx=None, sort_columns=False, kernel=0):
+def generate_raw(X, Y, p, n, polydeg, ops=REFERENCE_OPS, groups=None, ctx=None, sort_columns=False, kernel=0, variant=0):
     """colind [M, n] int64 (stencil order unless sort_columns), vals [nops, M, n]: the fixed-row CSR the kernels write."""
     ctx = ctx or default_context()
     X = _coords(X, "X")
@@ -315,7 +316,7 @@ def generate_raw(X, Y, p, n, polydeg, ops=REFERENCE_OPS, groups=None, ctx=None, 
         raise ValueError("DimensionMismatch: X and Y have different dimensions")
     N, dim = X.shape
     M = Y.shape[0]
-    opts = make_options(dim, p, n, polydeg, ops, 0, sort_columns, kernel)
+    opts = make_options(dim, p, n, polydeg, ops, 0, sort_columns, kernel, variant)
     colind = np.empty((M, n), np.int64)
     vals = np.empty((opts.nops, M, n), np.float64)
     g = None if groups is None else np.ascontiguousarray(groups, np.int32)
@@ -336,6 +337,22 @@ def generate_operator(X, Y, p, n, polydeg, X_idx_in=None, X_idx_bc=None, X_idx_b
     if X.shape[1] != 2:
         raise ValueError("the reference API is 2-D; use generate_raw(..., ops=...) for 3-D operator sets")
     colind, vals = generate_raw(X, Y, p, n, polydeg, REFERENCE_OPS, groups, ctx)
+    return tuple(_to_csc(colind, vals, shape, X.shape[0]))
+
+
+def generate_operator_collocated(X, p, n, polydeg, *, ctx=None, shape="reference"):
+    """-> (E, Dx, Dy, Dxx, Dyy, Dxy): the legacy 4-argument method generate_operator(X, p, n, polydeg)
+    (generate_operator.jl:354-491): unscaled stencils, centre at (eps, eps), RBF rows at X_j - x_c."""
+    X = _coords(X, "X")
+    colind, vals = generate_raw(X, None, p, n, polydeg, REFERENCE_OPS, None, ctx, variant=1)
+    return tuple(_to_csc(colind, vals, shape, X.shape[0]))
+
+
+def hyperviscosity_operator_collocated(k_deriv, X, p, n, polydeg, *, ctx=None, shape="reference"):
+    """-> (Dxk, Dyk): the legacy method hyperviscosity_operator(K, X, p, n, polydeg) (hyperviscosity_operator.jl:314-440)."""
+    X = _coords(X, "X")
+    ops = [("Dk", a, int(k_deriv)) for a in range(X.shape[1])]
+    colind, vals = generate_raw(X, None, p, n, polydeg, ops, None, ctx, variant=1)
     return tuple(_to_csc(colind, vals, shape, X.shape[0]))
 
 

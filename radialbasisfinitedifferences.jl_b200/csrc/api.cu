@@ -253,6 +253,7 @@ int rbffd_generate_operator_host(rbffd_context* ctx, const rbffd_options* opts, 
     if (!X || N < 1) RBFFD_FAIL(ctx, RBFFD_ERR_INVALID, "generate_operator: X is empty");
     if (!colind_out || !vals_out) RBFFD_FAIL(ctx, RBFFD_ERR_INVALID, "generate_operator: NULL output buffer");
     if (!Y) { Y = X; M = N; }
+    if (opts->variant != 0 && (Y != X || M != N)) RBFFD_FAIL(ctx, RBFFD_ERR_INVALID, "the legacy collocated variant takes X only (pass Y = NULL)");
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
     const int dim = opts->dim, n = opts->n;

@@ -150,6 +150,7 @@ int rbffd_validate_options(rbffd_context* ctx, const rbffd_options* o) {
     int rc = build_op_tables(o, &T, msg, sizeof(msg));
     if (rc != RBFFD_OK) RBFFD_FAIL(ctx, rc, "%s", msg);
     if (o->index_base != 0 && o->index_base != 1) RBFFD_FAIL(ctx, RBFFD_ERR_INVALID, "index_base must be 0 or 1");
+    if (o->variant != 0 && o->variant != 1) RBFFD_FAIL(ctx, RBFFD_ERR_INVALID, "variant must be 0 (two-set methods) or 1 (legacy collocated methods)");
     return RBFFD_OK;
 }
 
@@ -168,6 +169,7 @@ struct WArgs {
     int32_t* colind;           // [M][n]
     double* vals;              // [nops][M][n]
     int* fail;                 // first singular node + 1 (atomicMin over 0x7fffffff)
+    int variant;               // 1: legacy collocated methods (generate_operator.jl:354-491, hyperviscosity_operator.jl:314-440)
     OpTables T;
 };
 
@@ -233,12 +235,12 @@ __global__ void __launch_bounds__(128) weights_generic_kernel(WArgs a, int warps
 #pragma unroll
         for (int c = 0; c < D; ++c) {
             for (int o = 16; o > 0; o >>= 1) mx[c] = fmax(mx[c], __shfl_xor_sync(FULL, mx[c], o));
-            s[c] = 1.0 / mx[c];
+            s[c] = a.variant ? 1.0 : 1.0 / mx[c];                 // legacy method: stencils are not scaled (:403-406)
         }
         __syncwarp();
         for (int j = lane; j < n; j += 32) {
 #pragma unroll
-            for (int c = 0; c < D; ++c) S[j * D + c] = S[j * D + c] * s[c];
+            for (int c = 0; c < D; ++c) S[j * D + c] = (a.variant && j == 0) ? EPS : S[j * D + c] * s[c];   // legacy: centre := (eps, eps) (:410)
         }
         __syncwarp();
         // ---- interpolationmatrix.jl:5 : A = [Phi P; P' 0] ----
@@ -317,13 +319,14 @@ __global__ void __launch_bounds__(128) weights_generic_kernel(WArgs a, int warps
             const int64_t row = a.rows[rr];
             double eta[D];
 #pragma unroll
-            for (int c = 0; c < D; ++c) eta[c] = (a.Y[row * D + c] - xc[c]) * s[c];
+            for (int c = 0; c < D; ++c) eta[c] = a.variant ? EPS : (a.Y[row * D + c] - xc[c]) * s[c];   // legacy: polynomial rows at X_shift[1] (:429)
             for (int j = lane; j < n; j += 32) {
                 double del[D];
 #pragma unroll
                 for (int c = 0; c < D; ++c) {
                     double t = eta[c] - S[j * D + c];
                     del[c] = t == 0.0 ? EPS : t;     // generate_operator.jl:127-132
+                    if (a.variant) del[c] = S[j * D + c];          // legacy: RBF rows at X_shift[j] = X_j - x_c (:433)
                 }
                 for (int o = 0; o < nops; ++o) rhs[o * m + j] = rhs_rbf_entry<D>(T, o, del, s);
             }
@@ -453,7 +456,9 @@ int rbffd_weights_impl(rbffd_context* ctx, const rbffd_options* opts, const doub
 
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev[4], st));
     int rc = RBFFD_ERR_UNSUPPORTED;
-    if (identity && opts->kernel != 1) {
+    a.variant = opts->variant;
+    if (opts->variant != 0 && opts->kernel > 1) RBFFD_FAIL(ctx, RBFFD_ERR_UNSUPPORTED, "the legacy collocated variant runs on the generic kernel only");
+    if (identity && opts->kernel != 1 && opts->variant == 0) {
         if (opts->kernel != 2) {
             rc = rbffd_weights_ns(ctx, T, X, N, Y, M, stencils, colind_out, vals_out, flags.p);
             if (rc == RBFFD_ERR_UNSUPPORTED && T.n > 32) rc = rbffd_weights_nsw(ctx, T, X, N, Y, M, stencils, colind_out, vals_out);

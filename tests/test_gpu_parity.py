@@ -447,3 +447,23 @@ def test_peer_memory_halo_exchange_two_gpus():
                        env={**os.environ, "HALO_G": "200"})
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "OK" in r.stdout
+
+
+@pytest.mark.gpu
+def test_legacy_collocated_methods(ctx, oracle):
+    """generate_operator(X, p, n, polydeg) / hyperviscosity_operator(K, X, p, n, polydeg) (generate_operator.jl:354,
+    hyperviscosity_operator.jl:314): unscaled stencils, centre at (eps, eps), RBF rows at X_j - x_c.  variant = 1."""
+    X = rb.nodes.jittered_lattice(2, 40, seed=5)
+    ops = ["E", "Dx", "Dy", "Dxx", "Dyy", "Dxy", ("Dk", 0, 2), ("Dk", 1, 2)]
+    colind, vals = rb.generate_raw(X, None, 3, 20, 3, ops, ctx=ctx, variant=1)
+    rcol, rvals, cond = oracle.generate_operator_collocated(X, 3, 20, 3, ops=ops, want_cond=True)
+    assert np.array_equal(colind, rcol)
+    _check_weights(vals, rvals, cond, ops)
+    E, Dx, Dy, Dxx, Dyy, Dxy = rb.generate_operator_collocated(X, 3, 20, 3, ctx=ctx)
+    Dxk, Dyk = rb.hyperviscosity_operator_collocated(2, X, 3, 20, 3, ctx=ctx)
+    assert abs(Dxk - Dxx).max() <= 1e-9 * abs(Dxx).max() and abs(Dyk - Dyy).max() <= 1e-9 * abs(Dyy).max()
+    assert np.allclose(np.asarray(E.sum(1)).ravel(), 1.0, atol=1e-8)
+    with pytest.raises(rb.RbffdError):
+        rb.generate_raw(X, X + 1e-3, 3, 20, 3, ["E"], ctx=ctx, variant=1)        # the legacy methods take X only
+    with pytest.raises(rb.RbffdError):
+        rb.generate_raw(X, None, 3, 20, 3, ["E"], ctx=ctx, variant=1, kernel=3)

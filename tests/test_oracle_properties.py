@@ -155,3 +155,73 @@ def test_spmv_and_rhs_oracle_against_scipy(oracle):
     want = E.T @ (a * (Dxx @ u) + a * (Dyy @ u) - ux * (Dx @ u) - uy * (Dy @ u)) - gam * ((Dxk + Dyk) @ u)
     got = oracle.rhs_advdiff(colind, *mats, a, ux, uy, gam, u)
     assert np.allclose(got, want, rtol=1e-12, atol=1e-12)
+
+
+def _legacy_numpy(X, idx, p, polydeg):
+    """Line-by-line numpy replay of generate_operator(X, p, n, polydeg) (src/generate_operator.jl:388-468) for one
+    stencil at a time: X_shift with the centre at (eps, eps), A = [Phi P; P' 0] unscaled, inv(A) * RHS with the
+    Symbolics closed forms written out (comments at :139-153)."""
+    eps = np.finfo(float).eps
+    ex = [(a, g - a) for g in range(polydeg + 1) for a in range(g, -1, -1)]
+    out = np.zeros((6, len(X), idx.shape[1]))
+    for i in range(len(X)):
+        S = X[idx[i]] - X[idx[i][0]]
+        S[0] = eps
+        n = len(S)
+        d = S[:, None, :] - S[None, :, :]
+        Phi = np.sqrt((d ** 2).sum(-1)) ** p
+        P = np.stack([S[:, 0] ** a * S[:, 1] ** b for a, b in ex], 1)
+        q = P.shape[1]
+        A = np.block([[Phi, P], [P.T, np.zeros((q, q))]])
+        x, y = S[:, 0], S[:, 1]
+        r = np.hypot(x, y)
+        b = r ** p
+        bx, by = p * x * r ** (p - 2), p * y * r ** (p - 2)
+        bxx = p * r ** (p - 2) + p * (p - 2) * x ** 2 * r ** (p - 4)
+        byy = p * r ** (p - 2) + p * (p - 2) * y ** 2 * r ** (p - 4)
+        bxy = p * (p - 2) * x * y * r ** (p - 4)
+
+        def mono(a, b_, da, db):
+            if a < da or b_ < db:
+                return 0.0
+            ca = np.prod([a - t for t in range(da)]) if da else 1.0
+            cb = np.prod([b_ - t for t in range(db)]) if db else 1.0
+            return ca * cb * eps ** (a - da) * eps ** (b_ - db)
+        rows = []
+        for (da, db), rb_ in (((0, 0), b), ((1, 0), bx), ((0, 1), by), ((2, 0), bxx), ((0, 2), byy), ((1, 1), bxy)):
+            rows.append(np.concatenate([rb_, [mono(a, b_, da, db) for a, b_ in ex]]))
+        W = np.linalg.inv(A) @ np.stack(rows, 1)
+        out[:, i, :] = W[:n].T
+    return out
+
+
+def test_legacy_collocated_method(oracle):
+    """generate_operator(X, p, n, polydeg) (generate_operator.jl:354-491): the oracle's variant 1 against a literal numpy
+    replay, polynomial reproduction of every operator (the constraint rows hold whatever the RBF rows are), and the sign
+    quirk of the odd-derivative RBF rows relative to the two-set method."""
+    X = rb.nodes.jittered_lattice(2, 14, seed=4)
+    p, n, deg = 3, 16, 2
+    idx, vals, cond = oracle.generate_operator_collocated(X, p, n, deg, want_cond=True)
+    ref = _legacy_numpy(X, idx, p, deg)
+    tol = 200 * np.finfo(float).eps * cond[:, None]
+    for o in range(6):
+        assert np.all(np.abs(vals[o] - ref[o]) <= tol * np.abs(ref[o]).max(1, keepdims=True))
+    # polynomial reproduction at the centre: sum_j w_j mono(X_j - x_c) = (L mono)(0) up to the (eps, eps) shift
+    names = ["E", "Dx", "Dy", "Dxx", "Dyy", "Dxy"]
+    want = {"E": (0, 0), "Dx": (1, 0), "Dy": (0, 1), "Dxx": (2, 0), "Dyy": (0, 2), "Dxy": (1, 1)}
+    S = X[idx] - X[idx[:, :1]]
+    h = np.abs(S).max()
+    for o, nm in enumerate(names):
+        da, db = want[nm]
+        for a in range(deg + 1):
+            for b_ in range(deg + 1 - a):
+                lhs = (vals[o] * S[:, :, 0] ** a * S[:, :, 1] ** b_).sum(1)
+                exact = float(np.prod([a - t for t in range(da)]) * np.prod([b_ - t for t in range(db)])) if (a, b_) == (da, db) else 0.0
+                scale = np.abs(vals[o]).sum(1) * h ** (a + b_)
+                assert np.all(np.abs(lhs - exact) <= 1e3 * np.finfo(float).eps * cond * np.maximum(scale, 1.0))
+    # two-set method on the same nodes: even-order operators agree to truncation level, Dx/Dy differ (flipped RBF rows)
+    _, v2 = oracle.generate_operator(X, X, p, n, deg)
+    interior = np.all((X > 0.3) & (X < 0.7), axis=1)
+    rel = lambda a_, b_: np.abs(a_ - b_).max() / np.abs(b_).max()
+    assert rel(vals[3][interior], v2[3][interior]) < 0.2          # Dxx: same operator up to the anisotropic-scaling effect
+    assert rel(vals[1][interior], v2[1][interior]) > 1e-3         # Dx: the sign quirk is really there
