@@ -1,11 +1,12 @@
 #!/usr/bin/env python
 """Device-resident advection-diffusion with hyperviscosity: the B200 counterpart of examples/adv_diff_test.jl.
 
-The reference script reads a CGNS mesh (out of scope: no HDF5 reader here), builds E, Dx, Dy, Dxx, Dyy and the
-hyperviscosity pair with the boundary-aware methods, and integrates `cons_sys` with SSPRK43.  Here the node set is a
-synthetic rectangle [0,5]x[0,1] (interior jittered lattice + boundary midpoints + ghost nodes offset along the outward
-normal, the layout src/processmesh.jl:174-186 produces), every operator is generated on the GPU in ONE call (one kNN,
-one factorisation per node, 7 right-hand sides) and stays in HBM; each RK stage is
+The reference script reads a CGNS mesh, builds E, Dx, Dy, Dxx, Dyy and the hyperviscosity pair with the boundary-aware
+methods, and integrates `cons_sys` with SSPRK43.  With `--mesh file.cgns` the node set comes from the same mesh through
+rb.mesh.processmesh (BASELINE config 1: examples/rect_0_10.cgns, markers left/right/top/bottom, adv_diff_test.jl:24-29);
+without it the node set is a synthetic rectangle [0,5]x[0,1] (interior jittered lattice + boundary midpoints + ghost
+nodes offset along the outward normal, the layout src/processmesh.jl:174-186 produces).  Every operator is generated on
+the GPU in ONE call (one kNN, one factorisation per node, 7 right-hand sides) and stays in HBM; each RK stage is
     du = rhs_advdiff(u)           (rbffd_rhs_advdiff_device: fused multi-operator SpMV + E' + hyperviscosity)
     ghost update of u             (rbffd_bc_apply_device)
 on the device, the stage combinations are torch axpys.  SSP-RK3 with a fixed step stands in for the adaptive SSPRK43
@@ -44,10 +45,18 @@ def rectangle_nodes(gy, seed=0):
     return X, range(0, n_in), idx_bc, idx_g, h
 
 
-def run(gy=40, steps=50, verbose=True):
+def mesh_nodes(path, ctx=None):
+    """adv_diff_test.jl:24-29,78-85: nodes and index sets from the CGNS mesh, h = mean nearest-neighbour distance"""
+    X, _, idx_in, idx_bc, idx_g, _, _, _ = rb.mesh.processmesh(path, ["left", "right", "top", "bottom"], ctx=ctx)
+    d2 = ((X[:, None, :] - X[None, :, :]) ** 2).sum(-1)
+    np.fill_diagonal(d2, np.inf)
+    return X, idx_in, idx_bc, idx_g, float(np.sqrt(d2.min(1)).mean())
+
+
+def run(gy=40, steps=50, verbose=True, mesh=None):
     import torch
     dev = torch.device("cuda:0")
-    X, idx_in, idx_bc, idx_g, h = rectangle_nodes(gy)
+    X, idx_in, idx_bc, idx_g, h = mesh_nodes(mesh) if mesh else rectangle_nodes(gy)
     N = len(X)
     p, polydeg = 5, 5
     n = 2 * 21                                                           # adv_diff_test.jl:53-55
@@ -97,5 +106,6 @@ if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--gy", type=int, default=40)
     ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--mesh", default=None, help="CGNS mesh (e.g. tests/golden/rect_0_10.cgns = BASELINE config 1)")
     a = ap.parse_args()
-    run(a.gy, a.steps)
+    run(a.gy, a.steps, mesh=a.mesh)

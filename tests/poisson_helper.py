@@ -48,3 +48,44 @@ def poisson_error(tominec, gen):
     return np.linalg.norm(uY - ue) / np.linalg.norm(ue)
 
 
+
+
+def mesh_import_error(cgns_path, X, gen, ctx=None):
+    """test/mesh_import_test.jl:19-158 with `gen` standing in for generate_operator: Y comes from processmesh on the CGNS
+    mesh (ghost nodes dropped, :52), Neumann normals from the mesh (:38-40), p = 3, polydeg = 5, n = 42."""
+    import rbffd_b200 as rb
+    from scipy.spatial import cKDTree
+    Y_, _, iin, ibc, _, _, normals, _ = rb.mesh.processmesh(cgns_path, ["dirichlet", "neumann"], ctx=ctx)
+    iin, idi, ine = (np.arange(r.start, r.stop) for r in (iin, ibc[0], ibc[1]))
+    Y = np.concatenate([Y_[iin], Y_[idi], Y_[ine]])
+    assert iin[0] == 0 and idi[0] == len(iin) and ine[0] == len(iin) + len(idi)      # :52-54 keep the index sets valid
+    xn, yn = normals[1][:, 0], normals[1][:, 1]
+    X = X.copy()
+    N, M = len(X), len(Y)
+    nearest = cKDTree(Y).query(X, 1)[1]                                              # :57-68 (HNSW there; exact here)
+    for i in range(N):
+        Y[nearest[i]] = X[i]
+    p, polydeg = 3, 5
+    n = 2 * 21
+    colind, vals = gen(X, Y, p, n, polydeg)
+    E, Dx, Dy, Dxx, Dyy, Dxy = (csr(colind, v, N) for v in vals)
+    u_exact = lambda x, y: np.sin(2 * np.pi * x * y)
+    f2 = lambda x, y: -4.0 * x**2 * np.pi**2 * np.sin(2 * np.pi * x * y) - 4.0 * y**2 * np.pi**2 * np.sin(2 * np.pi * x * y)
+    f1 = lambda n1, n2, x, y: n2 * x * np.pi * np.cos(2 * np.pi * x * y) * 2.0 + n1 * y * np.pi * np.cos(2 * np.pi * x * y) * 2.0
+    D = np.zeros((M, N))
+    D[iin] = (Dxx + Dyy)[iin].toarray()
+    D[ine] = xn[:, None] * Dx[ine].toarray() + yn[:, None] * Dy[ine].toarray()
+    D[idi] = E[idi].toarray()
+    f = np.zeros(M)
+    f[iin] = f2(Y[iin, 0], Y[iin, 1])
+    f[ine] = f1(xn, yn, Y[ine, 0], Y[ine, 1])
+    f[idi] = u_exact(Y[idi, 0], Y[idi, 1])
+    h = np.mean(cKDTree(X).query(X, 2)[0][:, 1])
+    M0, M1, M2 = len(idi), len(ine), len(iin)
+    D[iin] *= 1 / np.sqrt(M2); f[iin] *= 1 / np.sqrt(M2)
+    D[ine] *= 1 / np.sqrt(M1); f[ine] *= 1 / np.sqrt(M1)
+    D[idi] *= 1 / h / np.sqrt(M0); f[idi] *= 1 / h / np.sqrt(M0)
+    u = np.linalg.lstsq(D, f, rcond=None)[0]
+    uY = E @ u
+    ue = u_exact(Y[:, 0], Y[:, 1])
+    return np.linalg.norm(uY - ue) / np.linalg.norm(ue)

@@ -220,6 +220,16 @@ def test_two_set_oversampled_poisson(ctx, oracle, tominec):
     assert abs(err - 0.0026579) < 2e-6
 
 
+def test_mesh_import_reference_test(ctx, tominec):
+    """test/mesh_import_test.jl:158 (err < 0.001) through the GPU path: CGNS mesh -> processmesh (exact GPU 1-NN for the
+    ghost offset and the normal orientation) -> generate_operator on the device -> the reference's least-squares solve."""
+    import os
+    from poisson_helper import mesh_import_error
+    path = os.path.join(os.path.dirname(__file__), "golden", "tominec_Y.cgns")
+    err = mesh_import_error(path, tominec["X"], lambda X, Y, p, n, deg: rb.generate_raw(X, Y, p, n, deg, ctx=ctx), ctx=ctx)
+    assert err < 0.001
+
+
 def test_hyperviscosity_reference_test(ctx, tominec):
     """test/hyperviscosity_test.jl:13-33 through the mirrored API (isapprox on sparse = Frobenius, rtol sqrt(eps))."""
     import scipy.sparse.linalg as spl
@@ -372,17 +382,26 @@ def test_ghost_node_boundary_updates(ctx):
     assert np.max(np.abs((D[1] @ got)[np.array(idx_bc[3])])) <= 1e-8 * np.abs(D[1]).max()
 
 
-def test_device_resident_time_stepping_example(oracle):
+@pytest.mark.parametrize("mesh", [None, "rect_0_10.cgns"])
+def test_device_resident_time_stepping_example(oracle, mesh):
     """examples/adv_diff_b200.py (generate -> RHS -> ghost updates -> SSP-RK3, all on the device) against the same
-    scheme driven by the CPU oracle's operators and a NumPy restatement of the ghost updates."""
+    scheme driven by the CPU oracle's operators and a NumPy restatement of the ghost updates.  mesh = rect_0_10.cgns is
+    BASELINE config 1 (examples/adv_diff_test.jl on the coarsest mesh, node set through rb.mesh.processmesh)."""
     import importlib.util, os
     import scipy.sparse as sp
     spec = importlib.util.spec_from_file_location("adv_diff_b200", os.path.join(os.path.dirname(__file__), "..", "examples", "adv_diff_b200.py"))
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
     gy, steps = 16, 12
-    X, u, (idx_in, idx_bc, idx_g) = mod.run(gy=gy, steps=steps, verbose=False)
-    N, n, h = len(X), 42, 1.0 / gy
+    if mesh:
+        path = os.path.join(os.path.dirname(__file__), "golden", mesh)
+        X, u, (idx_in, idx_bc, idx_g) = mod.run(steps=steps, verbose=False, mesh=path)
+        h = mod.mesh_nodes(path)[4]
+        assert len(X) == 1812 and len(idx_in) == 1572                     # SURVEY.md §8: 1572 centroids + 120 BC + 120 ghosts
+    else:
+        X, u, (idx_in, idx_bc, idx_g) = mod.run(gy=gy, steps=steps, verbose=False)
+        h = 1.0 / gy
+    N, n = len(X), 42
     groups = ((idx_in.start, idx_in.stop), [(r.start, r.stop) for r in idx_bc], [(r.start, r.stop) for r in idx_g])
     names = ["E", "Dx", "Dy", "Dxx", "Dyy", ("Dk", 0, 4), ("Dk", 1, 4)]
     colind, vals = oracle.generate_operator(X, X, 5, n, 5, groups=groups, ops=names, mode=0)

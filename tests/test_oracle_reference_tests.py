@@ -3,12 +3,18 @@
 The reference has no golden index/weight vectors; what it asserts is
   * test/poisson_test.jl:132        relative l2 error of the oversampled Poisson solve < 0.0027
   * test/hyperviscosity_test.jl:32  hyperviscosity_operator(2, ...) ~ Dxx, Dyy (Frobenius isapprox, rtol sqrt(eps))
-Both are replayed here on the reference's own node sets (tests/golden/tominec_fitted.npz).
+  * test/mesh_import_test.jl:158    the same Poisson problem with Y from processmesh on data/tominec_Y.cgns, err < 0.001
+All three are replayed here on the reference's own node sets (tests/golden/tominec_fitted.npz, tests/golden/*.cgns).
 """
 import numpy as np
 
 
+import os
+
+from poisson_helper import mesh_import_error as _mesh_import_error
 from poisson_helper import poisson_error as _poisson_error
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
 def test_poisson_known_answer(tominec, oracle):
@@ -33,3 +39,33 @@ def test_hyperviscosity_k2_equals_second_derivatives(tominec, oracle):
     for got, ref in ((vk[0], vals[3]), (vk[1], vals[4])):
         assert np.linalg.norm(got - ref) <= rtol * max(np.linalg.norm(got), np.linalg.norm(ref))
         assert np.linalg.norm(got - ref) <= 1e-11 * np.linalg.norm(ref)    # probe: 3e-14
+
+
+def test_mesh_import_known_answer(tominec, oracle):
+    """test/mesh_import_test.jl:19-158: CGNS -> processmesh -> oversampled Poisson solve (p=3, polydeg=5, n=42)."""
+    err = _mesh_import_error(os.path.join(GOLDEN, "tominec_Y.cgns"), tominec["X"],
+                             lambda X, Y, p, n, deg: oracle.generate_operator(X, Y, p, n, deg, mode=0))
+    assert err < 0.001                                        # the reference's own assertion
+    assert abs(err - 0.00047039) < 5e-6                       # value obtained with exact nearest neighbours (HNSW in the reference)
+
+
+def test_processmesh_on_reference_meshes():
+    """src/processmesh.jl on examples/rect_0_10.cgns (BASELINE config 1) through the minimal HDF5 reader."""
+    import numpy as np
+    import rbffd_b200 as rb
+    h5 = rb.mesh.Hdf5File(os.path.join(GOLDEN, "rect_0_10.cgns"))
+    assert {"GridCoordinates", "TriElements", "left", "right", "top", "bottom"} <= set(h5.keys("Base/dom-1"))     # dense (fractal-heap) group
+    x = h5["Base/dom-1/GridCoordinates/CoordinateX/ data"]
+    assert x.shape == (847,) and x.min() == 0.0 and x.max() == 5.0      # SURVEY.md §8: 847 vertices, x in [0, 5]
+    Y, P, iin, ibc, ig, cells, nrm, tan = rb.mesh.processmesh(os.path.join(GOLDEN, "rect_0_10.cgns"), ["left", "right", "top", "bottom"])
+    assert Y.shape == (1812, 2) and len(iin) == 1572 and sum(len(r) for r in ibc) == 120 and sum(len(r) for r in ig) == 120
+    assert not np.isnan(Y).any()
+    for b, outward in enumerate([(-1, 0), (1, 0), (0, 1), (0, -1)]):   # normals point out of [0,5] x [0,1]
+        assert np.allclose(nrm[b], outward)
+        assert np.allclose(np.abs(tan[b]), np.abs(np.array(outward)[::-1]))
+        g, bc = Y[ig[b].start:ig[b].stop], Y[ibc[b].start:ibc[b].stop]
+        off = ((g - bc) * np.array(outward)).sum(1)
+        assert np.allclose(off, off[0]) and 0.01 < off[0] < 0.05          # one offset for all ghosts: mean BC -> interior distance
+    assert np.all(Y[iin.start:iin.stop].min(0) > 0) and np.all(Y[iin.start:iin.stop].max(0) < (5, 1))
+    tri, edges = cells
+    assert tri.shape == (1572, 3) and edges.shape == (120, 2) and tri.min() == 0 and tri.max() == 846
