@@ -520,7 +520,7 @@ int orc_weights(const double* X, int64_t N, int d, const double* Y, int64_t M,
         int* piv = (int*)malloc(sizeof(int) * (size_t)m);
 #pragma omp for schedule(dynamic, 64)
         for (int64_t i = 0; i < N; ++i) {
-            if (start[i + 1] == start[i] && !cond1) continue;
+            if (start[i + 1] == start[i]) { if (cond1) cond1[i] = 0.0; continue; }   /* no row uses this stencil */
             const int64_t* st = idx + i * n;
             double s[3] = {1.0, 1.0, 1.0};
             const double* xc = X + st[0] * d;
