@@ -24,6 +24,7 @@
 // polydeg >= (p-1)/2.   Replaces the same reference lines as weights.cu.
 #include "common.cuh"
 #include "tables.cuh"
+#include "phs.cuh"
 
 namespace {
 
@@ -49,18 +50,6 @@ __device__ __forceinline__ void dmma884n(double& c0, double& c1, double a, doubl
                  : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
-// 1/sqrt(x), x > 0, to ~1 ulp: MUFU.RSQ64H seed (relative error ~2^-20) + one third-order step
-// y (1 + e/2 + 3 e^2/8), e = 1 - x y^2
-__device__ __forceinline__ double fast_rsqrt(double x) {
-    double y;
-    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-    const double t = x * y;
-    const double e = fma(-t, y, 1.0);
-    double u = fma(e, 0.375, 0.5);
-    u = u * e;
-    return fma(y, u, y);
-}
-
 // 1/x to ~1 ulp: MUFU.RCP64H seed (relative error ~2^-20) + one third-order step y (1 + e + e^2), e = 1 - x y
 __device__ __forceinline__ double rcp3(double x) {
     double y;
@@ -70,19 +59,6 @@ __device__ __forceinline__ double rcp3(double x) {
     return fma(y, u, y);
 }
 
-// r^p = r2^((p+1)/2) / r for odd p, hp = (p-1)/2; straight-line for p = 3, 5, 7, 9 (warp-uniform selects)
-__device__ __forceinline__ double phs_pow(double r2, double y, int hp) {
-    if (hp == 0) return r2 * y;                         // p = 1
-    const double r4 = r2 * r2;
-    double v = r4 * y;                                  // r^3
-    if (hp <= 4) {
-        const double m = (hp & 1) ? 1.0 : r2;           // p = 5, 9: one more r2
-        const double q4 = hp >= 3 ? r4 : 1.0;           // p = 7, 9: one more r^4
-        return hp == 1 ? v : v * (m * q4);
-    }
-    for (int e = 1; e < hp; ++e) v *= r2;
-    return v;
-}
 // max over the warp of a non-negative double: ordering of non-negative doubles == ordering of their bit patterns
 __device__ __forceinline__ double warp_max_nonneg(double v) {
     const unsigned hi = (unsigned)__double2hiint(v), lo = (unsigned)__double2loint(v);
@@ -270,53 +246,20 @@ __global__ void __launch_bounds__(128, MINB) weights_ns_kernel(NArgs a) {
                 del[c] = dd == 0.0 ? EPS : dd;
                 r2 = fma(del[c], del[c], r2);
             }
-            const double y = fast_rsqrt(r2);
+            const double y = phs_rsqrt(r2);
             double rp4 = y;                                     // r^(p-4)
             for (int e = 1; e < hp; ++e) rp4 *= r2;
             const double rp2 = rp4 * r2, rp = rp2 * r2, r = r2 * y;
             for (int o = 0; o < nops; ++o) Bt[pos * BS + o] = rhs_rbf_entry_fast<D>(T, o, del, s, r, r2, rp, rp2, rp4);
         }
         __syncwarp();
-        // ---- 3. Phi~ in permuted order, by symmetric pairs ----
-        // lane l owns position l; in round k it pairs with position (l + k) mod n.  Rounds 1 .. n/2 visit every
-        // unordered pair (the last round of an even n visits its pairs twice, with identical values).  Coincident
-        // nodes give r2 = 0 -> NaN, which the finiteness check of the weights turns into the pivoted fallback.
+        // ---- 3. Phi~ in permuted order, by symmetric pairs (phs.cuh): lane l owns position l ----
         {
             double me[D];
             const int l = lane < n ? lane : 0;
 #pragma unroll
             for (int c = 0; c < D; ++c) me[c] = Sc[l * DP + c];
-            double* const grow_l = G + l * LD;
-            double* const gcol_l = G + l;
-            const int rounds = n >> 1;
-            auto phi = [&](int k, int& ib) -> double {
-                ib = l + k;
-                ib = ib >= n ? ib - n : ib;
-                double o[D];
-                if constexpr (D == 2) {
-                    const double2 v = *reinterpret_cast<const double2*>(Sc + ib * DP);
-                    o[0] = v.x; o[1] = v.y;
-                } else {
-                    const double2 v = *reinterpret_cast<const double2*>(Sc + ib * DP);
-                    o[0] = v.x; o[1] = v.y; o[2] = Sc[ib * DP + 2];
-                }
-                double r2 = 0.0;
-#pragma unroll
-                for (int c = 0; c < D; ++c) { const double dd = me[c] - o[c]; r2 = fma(dd, dd, r2); }
-                return phs_pow(r2, fast_rsqrt(r2), hp);
-            };
-            int k = 1;
-            for (; k + 1 <= rounds; k += 2) {                   // two independent dependency chains per trip
-                int b0, b1;
-                const double v0 = phi(k, b0);
-                const double v1 = phi(k + 1, b1);
-                if (lane < n) { grow_l[b0] = v0; gcol_l[b0 * LD] = v0; grow_l[b1] = v1; gcol_l[b1 * LD] = v1; }
-            }
-            if (k <= rounds) {
-                int b0;
-                const double v0 = phi(k, b0);
-                if (lane < n) { grow_l[b0] = v0; gcol_l[b0 * LD] = v0; }
-            }
+            phs_assemble<D, DP, LD>(Sc, G, me, l, n, lane < n, hp);
         }
         __syncwarp();
         // ---- 4. Y = Phi~[:, N] - Phi~[:, B] W   (4 x NJ tiles; the right-hand-side columns start from b and use w_p) ----

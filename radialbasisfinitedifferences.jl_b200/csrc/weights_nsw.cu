@@ -22,6 +22,7 @@
 
 #include "common.cuh"
 #include "tables.cuh"
+#include "phs.cuh"
 
 namespace {
 
@@ -44,34 +45,12 @@ __device__ __forceinline__ void dmma884w(double& c0, double& c1, double a, doubl
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
                  : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
-__device__ __forceinline__ double rsqrt3(double x) {       // see weights_ns.cu
-    double y;
-    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-    const double t = x * y;
-    const double e = fma(-t, y, 1.0);
-    double u = fma(e, 0.375, 0.5);
-    u = u * e;
-    return fma(y, u, y);
-}
 __device__ __forceinline__ double rcp3w(double x) {
     double y;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
     const double e = fma(-x, y, 1.0);
     const double u = fma(e, e, e);
     return fma(y, u, y);
-}
-// r^p = r2^((p+1)/2) / r for odd p, hp = (p-1)/2; straight-line for p = 3, 5, 7, 9 (warp-uniform selects)
-__device__ __forceinline__ double phs_pow(double r2, double y, int hp) {
-    if (hp == 0) return r2 * y;                         // p = 1
-    const double r4 = r2 * r2;
-    double v = r4 * y;                                  // r^3
-    if (hp <= 4) {
-        const double m = (hp & 1) ? 1.0 : r2;           // p = 5, 9: one more r2
-        const double q4 = hp >= 3 ? r4 : 1.0;           // p = 7, 9: one more r^4
-        return hp == 1 ? v : v * (m * q4);
-    }
-    for (int e = 1; e < hp; ++e) v *= r2;
-    return v;
 }
 __device__ __forceinline__ double warp_max_nn(double v) {
     const unsigned hi = (unsigned)__double2hiint(v), lo = (unsigned)__double2loint(v);
@@ -292,40 +271,14 @@ __global__ void __launch_bounds__(128, 4) weights_nsw_kernel(WNArgs a) {
                     del[c] = dd == 0.0 ? EPS : dd;
                     r2 = fma(del[c], del[c], r2);
                 }
-                const double y = rsqrt3(r2);
+                const double y = phs_rsqrt(r2);
                 double rp4 = y;                                 // r^(p-4)
                 for (int e = 1; e < hp; ++e) rp4 *= r2;
                 const double rp2 = rp4 * r2, rp = rp2 * r2, r = r2 * y;
                 for (int o = 0; o < nops; ++o) Bt[L2 * BS + o] = rhs_rbf_entry_fast<D>(T, o, del, s, r, r2, rp, rp2, rp4);
             }
             bar_named(2, 64);
-            double* const grow_l = G + l * LD;
-            double* const gcol_l = G + l;
-            const int rounds = n >> 1;
-            auto phi = [&](int k, int& ib) -> double {
-                ib = l + k;
-                ib = ib >= n ? ib - n : ib;
-                double o[D];
-                const double2 v = *reinterpret_cast<const double2*>(Sc + ib * DP);
-                o[0] = v.x; o[1] = v.y;
-                if constexpr (D == 3) o[2] = Sc[ib * DP + 2];
-                double r2 = 0.0;
-#pragma unroll
-                for (int c = 0; c < D; ++c) { const double dd = sx[c] - o[c]; r2 = fma(dd, dd, r2); }
-                return phs_pow(r2, rsqrt3(r2), hp);
-            };
-            int k = 1;
-            for (; k + 1 <= rounds; k += 2) {
-                int b0, b1;
-                const double v0 = phi(k, b0);
-                const double v1 = phi(k + 1, b1);
-                if (L2 < n) { grow_l[b0] = v0; gcol_l[b0 * LD] = v0; grow_l[b1] = v1; gcol_l[b1 * LD] = v1; }
-            }
-            if (k <= rounds) {
-                int b0;
-                const double v0 = phi(k, b0);
-                if (L2 < n) { grow_l[b0] = v0; gcol_l[b0 * LD] = v0; }
-            }
+            phs_assemble<D, DP, LD>(Sc, G, sx, l, n, L2 < n, hp);
         }
         __syncthreads();
         // ---- B. Y = Phi~[:, N] - Phi~[:, B] W : row tiles 2*warp, 2*warp+1; permutation applied while gathering ----
