@@ -106,6 +106,54 @@ __device__ __forceinline__ void mono_rows(const double* x, double* m, std::integ
     ((m[C] = (C == 0) ? 1.0 : m[MonoStep<D, C>::par] * x[MonoStep<D, C>::axis]), ...);
 }
 
+// Unpivoted elimination of one 48 x 4 panel of the definite matrix S (static pivot rows pr0 .. pr0+3), one warp, two rows
+// per lane (rows lane and lane + 32).  Pbuf [4][PS] holds the panel by column; the transform columns W of the rank-4
+// update X += W X[pivots, :] go to Lb [4][PS], the pivot reciprocals to rinv_s[pr0 ..].  Pivot rows are not scaled
+// (y = RHS_row / pivot at the end), so their own entry of W is zero.  Returns the sign-violation bits of the pivots.
+// Deliberately not inlined: it is called once per block step and would otherwise be replicated 12 times.
+__device__ __forceinline__ int gj_panel48(const double* __restrict__ Pbuf, double* __restrict__ Lb, double* __restrict__ rinv_s,
+                                       int pr0, int sgnbits, int PS) {
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const int sl = pr0 >> 5;                              // slot of the four pivot rows (pr0 is a multiple of 4)
+    double av[2][4], w[2][4];
+#pragma unroll
+    for (int rr = 0; rr < 2; ++rr)
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) {
+            av[rr][cc] = (rr == 0 || lane < 16) ? Pbuf[cc * PS + lane + 32 * rr] : 0.0;
+            w[rr][cc] = 0.0;
+        }
+    int bad = 0;
+#pragma unroll
+    for (int sidx = 0; sidx < 4; ++sidx) {
+        const int pl = (pr0 + sidx) & 31;
+        double pv[4], wp[4];
+#pragma unroll
+        for (int cc = sidx; cc < 4; ++cc) pv[cc] = __shfl_sync(FULL, sl ? av[1][cc] : av[0][cc], pl);
+#pragma unroll
+        for (int cc = 0; cc < sidx; ++cc) wp[cc] = __shfl_sync(FULL, sl ? w[1][cc] : w[0][cc], pl);
+        bad |= __double2hiint(pv[sidx]) ^ sgnbits;        // S not definite: the pivoted kernel must take over
+        const double rinv = rcp3w(pv[sidx]);
+        if (lane == 0) rinv_s[pr0 + sidx] = rinv;
+#pragma unroll
+        for (int rr = 0; rr < 2; ++rr) {
+            const double nl = (lane == pl && rr == sl) ? 0.0 : av[rr][sidx] * (-rinv);
+#pragma unroll
+            for (int cc = sidx + 1; cc < 4; ++cc) av[rr][cc] = fma(nl, pv[cc], av[rr][cc]);
+#pragma unroll
+            for (int cc = 0; cc < sidx; ++cc) w[rr][cc] = fma(nl, wp[cc], w[rr][cc]);
+            w[rr][sidx] = nl;
+        }
+    }
+#pragma unroll
+    for (int cc = 0; cc < 4; ++cc) {
+        Lb[cc * PS + lane] = w[0][cc];
+        if (lane < 16) Lb[cc * PS + lane + 32] = w[1][cc];
+    }
+    return bad;
+}
+
 constexpr int WN_LD = 65;      // row stride of Phi (original stencil order)
 constexpr int WN_NBP = 48;     // padded null-space dimension (6 tiles)
 
@@ -371,85 +419,73 @@ __global__ void __launch_bounds__(128, 4) weights_nsw_kernel(WNArgs a) {
             }
         }
         __syncthreads();                                  // the Y tile is dead: its storage becomes the exchange buffers
-        // ---- D. blocked Gauss-Jordan WITHOUT pivoting on the definite S (static pivot rows 4kb .. 4kb+3) ----
+        // ---- D. blocked Gauss-Jordan WITHOUT pivoting on the definite S (static pivot rows 4kb .. 4kb+3), with one
+        //         step of lookahead: in step kb the owner of panel kb+1 updates that tile column first and eliminates the
+        //         next panel while the other warps are still applying update kb ----
+        auto dump_panel = [&](auto JPc, auto Hc) {        // the 4 panel columns (tile column Jp, half h) of all 48 rows
+            constexpr int Jp = decltype(JPc)::value, h = decltype(Hc)::value, jp = Jp >> 2;
+            if ((t >> 1) == h) {
+                double* pw = Pbuf + (2 * (t & 1)) * PS + g;
 #pragma unroll
-        for (int kb = 0; kb < 12; ++kb) {
-            if (4 * kb < nb) {                            // block-uniform: identity-padded block steps are skipped
-                const int Jp = kb >> 1, h = kb & 1, owner = Jp & 3, jp = Jp >> 2;
-                const int jlo = h == 0 ? Jp : Jp + 1;
-                double* Lb = Lbuf + (kb & 1) * 4 * PS;
-                double* Ub = Ubuf + (kb & 1) * 4 * UST;
-                // raw pivot rows: tile row Jp, lanes with g>>2 == h, every warp for its own columns
-                if ((g >> 2) == h) {
-#pragma unroll
-                    for (int jj = 0; jj < 2; ++jj) {
-                        const int J = warp + 4 * jj;
-                        if (J >= jlo && (jj == 0 || has2))
-                            *reinterpret_cast<double2*>(Ub + (g & 3) * UST + 8 * J + 2 * t) = make_double2(c[Jp][jj][0], c[Jp][jj][1]);
-                    }
+                for (int I = 0; I < 6; ++I) {
+                    pw[8 * I] = c[I][jp][0];
+                    pw[PS + 8 * I] = c[I][jp][1];
                 }
-                if (warp == owner) {
-                    // the 4 panel columns (tile column Jp, half h) of all 48 rows, then two rows per lane
-                    if ((t >> 1) == h) {
-                        double* pw = Pbuf + (2 * (t & 1)) * PS + g;
-#pragma unroll
-                        for (int I = 0; I < 6; ++I) {
-                            pw[8 * I] = c[I][jp][0];
-                            pw[PS + 8 * I] = c[I][jp][1];
-                        }
-                    }
-                    __syncwarp();
-                    double av[2][4], w[2][4];
-#pragma unroll
-                    for (int rr = 0; rr < 2; ++rr)
-#pragma unroll
-                        for (int cc = 0; cc < 4; ++cc) {
-                            av[rr][cc] = (rr == 0 || lane < 16) ? Pbuf[cc * PS + lane + 32 * rr] : 0.0;
-                            w[rr][cc] = 0.0;
-                        }
-#pragma unroll
-                    for (int sidx = 0; sidx < 4; ++sidx) {
-                        const int pr = 4 * kb + sidx;     // static pivot row: lane pr & 31, slot pr >> 5
-                        const int pl = pr & 31, sl = pr >> 5;
-                        double pv[4], wp[4];
-#pragma unroll
-                        for (int cc = sidx; cc < 4; ++cc) pv[cc] = __shfl_sync(FULL, av[sl][cc], pl);
-#pragma unroll
-                        for (int cc = 0; cc < sidx; ++cc) wp[cc] = __shfl_sync(FULL, w[sl][cc], pl);
-                        bad |= __double2hiint(pv[sidx]) ^ sgnbits;    // S not definite: the pivoted kernel must take over
-                        const double rinv = rcp3w(pv[sidx]);
-                        if (lane == 0) rinv_s[pr] = rinv;
-#pragma unroll
-                        for (int rr = 0; rr < 2; ++rr) {
-                            const double nl = (lane == pl && rr == sl) ? 0.0 : av[rr][sidx] * (-rinv);
-#pragma unroll
-                            for (int cc = sidx + 1; cc < 4; ++cc) av[rr][cc] = fma(nl, pv[cc], av[rr][cc]);
-#pragma unroll
-                            for (int cc = 0; cc < sidx; ++cc) w[rr][cc] = fma(nl, wp[cc], w[rr][cc]);
-                            w[rr][sidx] = nl;
-                        }
-                    }
-#pragma unroll
-                    for (int cc = 0; cc < 4; ++cc) {
-                        Lb[cc * PS + lane] = w[0][cc];
-                        if (lane < 16) Lb[cc * PS + lane + 32] = w[1][cc];
-                    }
-                }
-                __syncthreads();
-                double af[6];
-#pragma unroll
-                for (int I = 0; I < 6; ++I) af[I] = Lb[t * PS + 8 * I + g];
+            }
+            __syncwarp();
+        };
+        auto dump_pivot_rows = [&](auto KBc) {            // raw pivot rows of step kb: tile row kb>>1, lanes with g>>2 == kb&1
+            constexpr int kb = decltype(KBc)::value, Jp = kb >> 1, h = kb & 1, jlo = h == 0 ? Jp : Jp + 1;
+            double* Ub = Ubuf + (kb & 1) * 4 * UST;
+            if ((g >> 2) == h) {
 #pragma unroll
                 for (int jj = 0; jj < 2; ++jj) {
                     const int J = warp + 4 * jj;
-                    if (J >= jlo && (jj == 0 || has2)) {
-                        const double bf = Ub[t * UST + 8 * J + g];
-#pragma unroll
-                        for (int I = 0; I < 6; ++I) dmma884w(c[I][jj][0], c[I][jj][1], af[I], bf);
-                    }
+                    if (J >= jlo && (jj == 0 || has2))
+                        *reinterpret_cast<double2*>(Ub + (g & 3) * UST + 8 * J + 2 * t) = make_double2(c[Jp][jj][0], c[Jp][jj][1]);
                 }
             }
+        };
+        if (warp == 0) {
+            dump_panel(std::integral_constant<int, 0>{}, std::integral_constant<int, 0>{});
+            bad |= gj_panel48(Pbuf, Lbuf, rinv_s, 0, sgnbits, PS);
         }
+        dump_pivot_rows(std::integral_constant<int, 0>{});
+        __syncthreads();
+        auto gj_step = [&](auto KBc) {
+            constexpr int kb = decltype(KBc)::value;
+            constexpr int Jp = kb >> 1, h = kb & 1, jlo = h == 0 ? Jp : Jp + 1;
+            constexpr int kn = kb + 1, Jn = kn >> 1, hn = kn & 1, jn = Jn >> 2;      // next panel: tile column Jn, local index jn
+            const double* Lb = Lbuf + (kb & 1) * 4 * PS;
+            const double* Ub = Ubuf + (kb & 1) * 4 * UST;
+            const bool next = kn < 12 && 4 * kn < nb;
+            double af[6];
+#pragma unroll
+            for (int I = 0; I < 6; ++I) af[I] = Lb[t * PS + 8 * I + g];
+            auto update = [&](auto JJc) {
+                constexpr int jj = decltype(JJc)::value;
+                const int J = warp + 4 * jj;
+                if (J >= jlo && (jj == 0 || has2)) {
+                    const double bf = Ub[t * UST + 8 * J + g];
+#pragma unroll
+                    for (int I = 0; I < 6; ++I) dmma884w(c[I][jj][0], c[I][jj][1], af[I], bf);
+                }
+            };
+            if (next && warp == (Jn & 3)) {
+                update(std::integral_constant<int, jn>{});
+                dump_panel(std::integral_constant<int, Jn>{}, std::integral_constant<int, hn>{});
+                bad |= gj_panel48(Pbuf, Lbuf + (kn & 1) * 4 * PS, rinv_s, 4 * kn, sgnbits, PS);
+                update(std::integral_constant<int, 1 - jn>{});
+            } else {
+                update(std::integral_constant<int, 0>{});
+                update(std::integral_constant<int, 1>{});
+            }
+            if (next) dump_pivot_rows(std::integral_constant<int, (kn < 12 ? kn : 0)>{});
+            __syncthreads();
+        };
+        [&]<int... KB>(std::integer_sequence<int, KB...>) {
+            (([&] { if (4 * KB < nb) gj_step(std::integral_constant<int, KB>{}); }()), ...);
+        }(std::make_integer_sequence<int, 12>{});
         if (bad < 0 || kmin < 64u) *a.redo = 1;
         __syncthreads();                                  // every pivot reciprocal is published; Bt is dead (Ys aliases it)
         // y = RHS_row / pivot_row  (right-hand-side column rcb + o lives in tile (rcb + o) / 8)
