@@ -410,10 +410,10 @@ int rbffd_weights_fast(rbffd_context* ctx, const OpTables& T, const double* X, i
                        const int32_t* stencils, int32_t* colind_out, double* vals_out, int* fail_flag);
 // null-space path (weights_ns.cu): n <= 32, q <= 12; UNSUPPORTED also when a stencil fails its definiteness check
 int rbffd_weights_ns(rbffd_context* ctx, const OpTables& T, const double* X, int64_t N, const double* Y, int64_t M,
-                     const int32_t* stencils, int32_t* colind_out, double* vals_out, int* fail_flag);
+                     const int32_t* stencils, const int32_t* center, int32_t* colind_out, double* vals_out, int* fail_flag);
 // multi-warp null-space path (weights_nsw.cu): n <= 64, n - q <= 48; UNSUPPORTED also when a stencil fails its checks
 int rbffd_weights_nsw(rbffd_context* ctx, const OpTables& T, const double* X, int64_t N, const double* Y, int64_t M,
-                      const int32_t* stencils, int32_t* colind_out, double* vals_out);
+                      const int32_t* stencils, const int32_t* center, int32_t* colind_out, double* vals_out);
 // multi-warp register/DMMA path for 48 < m <= 96 (weights_mw.cu)
 int rbffd_weights_mw(rbffd_context* ctx, const OpTables& T, const double* X, int64_t N, const double* Y, int64_t M,
                      const int32_t* stencils, int32_t* colind_out, double* vals_out, int* fail_flag);
@@ -458,10 +458,19 @@ int rbffd_weights_impl(rbffd_context* ctx, const rbffd_options* opts, const doub
     int rc = RBFFD_ERR_UNSUPPORTED;
     a.variant = opts->variant;
     if (opts->variant != 0 && opts->kernel > 1) RBFFD_FAIL(ctx, RBFFD_ERR_UNSUPPORTED, "the legacy collocated variant runs on the generic kernel only");
+    // Y != X (generate_operator.jl:89-167, several rows per centre): the null-space kernels run one row per work item,
+    // reading the stencil of the row's centre (the elimination is repeated per row: still ~8x the generic kernel's rate)
+    const bool rowwise = !identity && opts->kernel != 1 && opts->kernel != 2 && opts->variant == 0;
+    if (rowwise) {
+        rc = rbffd_weights_ns(ctx, T, X, M, Y, M, stencils, center, colind_out, vals_out, flags.p);
+        if (rc == RBFFD_ERR_UNSUPPORTED && T.n > 32) rc = rbffd_weights_nsw(ctx, T, X, M, Y, M, stencils, center, colind_out, vals_out);
+        if (rc != RBFFD_OK && rc != RBFFD_ERR_UNSUPPORTED) return rc;
+        if (opts->kernel == 3 && rc != RBFFD_OK) RBFFD_FAIL(ctx, RBFFD_ERR_UNSUPPORTED, "null-space kernel not applicable (n=%d, q=%d) or a stencil failed its definiteness check", T.n, T.q);
+    }
     if (identity && opts->kernel != 1 && opts->variant == 0) {
         if (opts->kernel != 2) {
-            rc = rbffd_weights_ns(ctx, T, X, N, Y, M, stencils, colind_out, vals_out, flags.p);
-            if (rc == RBFFD_ERR_UNSUPPORTED && T.n > 32) rc = rbffd_weights_nsw(ctx, T, X, N, Y, M, stencils, colind_out, vals_out);
+            rc = rbffd_weights_ns(ctx, T, X, N, Y, M, stencils, nullptr, colind_out, vals_out, flags.p);
+            if (rc == RBFFD_ERR_UNSUPPORTED && T.n > 32) rc = rbffd_weights_nsw(ctx, T, X, N, Y, M, stencils, nullptr, colind_out, vals_out);
             if (rc != RBFFD_OK && rc != RBFFD_ERR_UNSUPPORTED) return rc;
             if (opts->kernel == 3 && rc != RBFFD_OK) RBFFD_FAIL(ctx, RBFFD_ERR_UNSUPPORTED, "null-space kernel not applicable (n=%d, q=%d) or a stencil failed its definiteness check", T.n, T.q);
         }

@@ -31,8 +31,9 @@ namespace {
 struct NArgs {
     const double* X;
     const double* Y;
-    const int32_t* stencils;   // [NS][n]
-    int64_t NS, M;
+    const int32_t* stencils;   // [NX][n]
+    const int32_t* center;     // [M] stencil of row i (Y != X: generate_operator.jl:47,103-108), or null: row i uses stencil i
+    int64_t NS, M;             // NS = rows processed (== M)
     int32_t* colind;           // [M][n]
     double* vals;              // [nops][M][n]
     int* fail;                 // flags[0]: singular node + 1
@@ -123,7 +124,7 @@ __global__ void __launch_bounds__(128, MINB) weights_ns_kernel(NArgs a) {
 
     for (int64_t i = blockIdx.x * 4ll + warp; i < a.NS; i += (int64_t)gridDim.x * 4) {
         // ---- 0. scalestencil.jl:10-20: lane l owns stencil node l ----
-        const int32_t* st = a.stencils + i * n;
+        const int32_t* st = a.stencils + (a.center ? (int64_t)a.center[i] : i) * n;
         const int id = st[lane < n ? lane : 0];
         double sx[D], s[D], eta[D];
         bool eta_zero = true;
@@ -490,7 +491,7 @@ bool table_matches(const OpTables& T) {
 // Null-space fast path.  Returns RBFFD_ERR_UNSUPPORTED when the configuration is outside its scope, or when any stencil
 // failed its definiteness / rank check (the caller then runs the pivoted Gauss-Jordan kernel over the batch).
 int rbffd_weights_ns(rbffd_context* ctx, const OpTables& T, const double* X, int64_t NS, const double* Y, int64_t M,
-                     const int32_t* stencils, int32_t* colind_out, double* vals_out, int* fail_flag) {
+                     const int32_t* stencils, const int32_t* center, int32_t* colind_out, double* vals_out, int* fail_flag) {
     const int nb = T.n - T.q;
     if (T.nops > 8 || T.n > 32 || nb < 1 || nb > NS_NB || T.dim < 2 || NS != M) return RBFFD_ERR_UNSUPPORTED;
     // conditional definiteness needs polynomial degree >= (p-1)/2: q >= C((p-1)/2 + d, d)
@@ -501,7 +502,7 @@ int rbffd_weights_ns(rbffd_context* ctx, const OpTables& T, const double* X, int
         if (T.q < need) return RBFFD_ERR_UNSUPPORTED;
     }
     NArgs a;
-    a.X = X; a.Y = Y; a.stencils = stencils; a.NS = NS; a.M = M;
+    a.X = X; a.Y = Y; a.stencils = stencils; a.center = center; a.NS = NS; a.M = M;
     a.colind = colind_out; a.vals = vals_out; a.fail = fail_flag; a.T = T;
     // d^alpha x^e (0) = alpha! [e == alpha]
     for (int o = 0; o < 8; ++o) { a.gzcol[o] = -1; a.gzval[o] = 0.0; }

@@ -29,7 +29,8 @@ namespace {
 struct WNArgs {
     const double* X;
     const double* Y;
-    const int32_t* stencils;   // [NS][n]
+    const int32_t* stencils;   // [NX][n]
+    const int32_t* center;     // [M] stencil of row i (Y != X), or null: row i uses stencil i
     int64_t NS, M;
     int32_t* colind;           // [M][n]
     double* vals;              // [nops][M][n]
@@ -208,7 +209,7 @@ __global__ void __launch_bounds__(128, 4) weights_nsw_kernel(WNArgs a) {
 
     for (int64_t i = blockIdx.x; i < a.NS; i += gridDim.x) {
         // ---- 0. scalestencil.jl:10-20: every warp reduces the whole stencil (identical s in all warps) ----
-        const int32_t* st = a.stencils + i * n;
+        const int32_t* st = a.stencils + (a.center ? (int64_t)a.center[i] : i) * n;
         const int id0 = st[lane < n ? lane : 0], id1 = st[lane + 32 < n ? lane + 32 : 0];
         double sx[D], s[D], eta[D];
         bool eta_zero = true;
@@ -574,7 +575,7 @@ int launch_nsw(rbffd_context* ctx, WNArgs& a) {
 // Multi-warp null-space path.  Returns RBFFD_ERR_UNSUPPORTED when the configuration is outside its scope, or when any
 // stencil failed its definiteness / rank / finiteness check (the caller then runs the pivoted kernels over the batch).
 int rbffd_weights_nsw(rbffd_context* ctx, const OpTables& T, const double* X, int64_t NS, const double* Y, int64_t M,
-                      const int32_t* stencils, int32_t* colind_out, double* vals_out) {
+                      const int32_t* stencils, const int32_t* center, int32_t* colind_out, double* vals_out) {
     const int nb = T.n - T.q;
     if (T.nops > 8 || T.n > 64 || T.n < 8 || T.n + T.nops > 64 || nb < 1 || nb > WN_NBP || T.dim < 2 || NS != M) return RBFFD_ERR_UNSUPPORTED;
     {
@@ -584,7 +585,7 @@ int rbffd_weights_nsw(rbffd_context* ctx, const OpTables& T, const double* X, in
         if (T.q < need) return RBFFD_ERR_UNSUPPORTED;
     }
     WNArgs a;
-    a.X = X; a.Y = Y; a.stencils = stencils; a.NS = NS; a.M = M;
+    a.X = X; a.Y = Y; a.stencils = stencils; a.center = center; a.NS = NS; a.M = M;
     a.colind = colind_out; a.vals = vals_out; a.T = T;
     for (int o = 0; o < 8; ++o) { a.gzcol[o] = -1; a.gzval[o] = 0.0; }
     for (int ax = 0; ax < 3; ++ax) a.lapcol[ax] = -1;

@@ -170,6 +170,29 @@ def test_multiwarp_nullspace_kernel_vs_oracle(ctx, oracle, d, g, p, deg, n, ops)
     _check_weights(v3, rvals, cond, ops)
 
 
+@pytest.mark.parametrize("d,g,p,deg,n,ops,over", [
+    (2, 40, 3, 3, 20, ["E", "Dx", "Dy", "Dxx", "Dyy", "Dxy"], 3),          # poisson_test.jl:56 (M ~ 3N), single-warp kernel
+    (2, 30, 5, 5, 42, ["E", "Dx", "Dy", "Dxx", "Dyy", "Dxy"], 2),          # mesh_import_test.jl parameters, multi-warp kernel
+    (3, 12, 7, 3, 60, ["Lap", "Dx", "Dz", "E"], 2)])                        # 3-D oversampled rows (n + nops <= 64)
+def test_oversampled_rows_through_nullspace_kernels(ctx, oracle, d, g, p, deg, n, ops, over):
+    """Y != X (generate_operator.jl:89-167) with kernel=3: one work item per Y row, reading the stencil of its nearest X
+    node and evaluating every right-hand side at eta = (Y_k - X_c) s != 0.  Checked against the oracle (same tolerance as
+    the collocated rows) and against the generic kernel that shares one factorisation per centre (kernel=1)."""
+    X = rb.nodes.jittered_lattice(d, g, seed=8)
+    rng = np.random.default_rng(3)
+    Y = rng.uniform(0.02, 0.98, size=(over * len(X), d))
+    Y[::7] = X[rng.integers(0, len(X), size=len(Y[::7]))]                   # some rows sit exactly on a node (eta == 0)
+    c3, v3 = rb.generate_raw(X, Y, p, n, deg, ops, ctx=ctx, kernel=3)
+    c1, v1 = rb.generate_raw(X, Y, p, n, deg, ops, ctx=ctx, kernel=1)
+    c0, v0 = rb.generate_raw(X, Y, p, n, deg, ops, ctx=ctx)
+    rcol, rvals, cond = oracle.generate_operator(X, Y, p, n, deg, ops=ops, mode=0, want_cond=True)
+    center = oracle.knn(X, Y, 1)[0][:, 0]
+    assert np.array_equal(c3, rcol) and np.array_equal(c1, rcol) and np.array_equal(c0, rcol)
+    _check_weights(v3, rvals, cond[center], ops)
+    _check_weights(v1, rvals, cond[center], ops)
+    assert np.array_equal(v0, v3)                                           # the automatic dispatch takes the null-space path
+
+
 def test_nullspace_kernel_falls_back_when_not_definite(ctx, oracle):
     """polydeg < (p-1)/2: Z'Phi Z is not definite, kernel=3 refuses and the automatic dispatch uses the pivoted kernels."""
     X = rb.nodes.jittered_lattice(2, 30, seed=8)
