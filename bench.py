@@ -390,6 +390,7 @@ def main():
             "knn": {"queries_per_s": M / t_k, "ms": t_k * 1e3},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_s * 1e3, "steps": Ke,
+                    "pcie_d2h_bytes_per_step": M * n * 4 + r * M * n * 8,
                     "call": "rbffd_generate_operator_host (pinned host X in, int64 colind + fp64 values out)"},
             "gpu_launches": int(launches),
             "clocks": clk,

@@ -5,6 +5,8 @@
 
 #include <chrono>
 #include <cstdlib>
+#include <thread>
+#include <emmintrin.h>
 
 #include "common.cuh"
 
@@ -128,6 +130,7 @@ int rbffd_destroy(rbffd_context* ctx) {
     for (int i = 0; i < 4; ++i) if (ctx->chunk_ev[i]) cudaEventDestroy(ctx->chunk_ev[i]);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->hflags) cudaFreeHost(ctx->hflags);
+    if (ctx->stage_i32) cudaFreeHost(ctx->stage_i32);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return RBFFD_OK;
@@ -246,6 +249,13 @@ int rbffd_weights_device(rbffd_context* ctx, const rbffd_options* opts, const do
     return rbffd_weights_impl(ctx, opts, X, N, Y, M, stencils, NS, center, colind_out, vals_out);
 }
 
+namespace {
+__global__ void init_deferred_kernel(int* f) { f[threadIdx.x] = (threadIdx.x & 7) == 0 ? 0x7fffffff : 0; }
+__global__ void pack_deferred_kernel(const int* f, int nchunks, int* out) {
+    if ((int)threadIdx.x < nchunks) { out[2 * threadIdx.x] = f[8 * threadIdx.x]; out[2 * threadIdx.x + 1] = f[8 * threadIdx.x + 4]; }
+}
+}  // namespace
+
 int rbffd_generate_operator_host(rbffd_context* ctx, const rbffd_options* opts, const double* X, int64_t N,
                                  const double* Y, int64_t M, const int32_t* xgroup, int64_t* colind_out, double* vals_out) {
     if (!ctx) return RBFFD_ERR_INVALID;
@@ -292,38 +302,161 @@ int rbffd_generate_operator_host(rbffd_context* ctx, const rbffd_options* opts, 
         DevBuf<int32_t> stencils;
         DevBuf<int64_t> c64;
         CUDA_TRY(ctx, stencils.alloc((size_t)N * n, st));
-        CUDA_TRY(ctx, c64.alloc((size_t)N * n, st));
         RBFFD_TRY(rbffd_stencils_impl(ctx, dX.p, N, dim, dX.p, N, n, xgroup ? dG.p : nullptr, stencils.p, nullptr, nullptr, nullptr));
-        const int64_t ch = ((M + nchunks - 1) / nchunks + 31) / 32 * 32;
+        // Row chunks shrink geometrically: big chunks first (few launch tails), small ones last (the copy of the last
+        // chunk is the only one that nothing overlaps).
+        int64_t cbeg[nchunks + 1];
+        {
+            static const double frac[nchunks] = {0.30, 0.24, 0.17, 0.12, 0.08, 0.05, 0.025, 0.015};
+            double acc = 0.0;
+            cbeg[0] = 0;
+            for (int k = 0; k < nchunks; ++k) {
+                acc += frac[k];
+                cbeg[k + 1] = k + 1 == nchunks ? M : std::min<int64_t>(M, (int64_t)(acc * (double)M) / 32 * 32);
+            }
+        }
+        int64_t ch = 0;
+        for (int k = 0; k < nchunks; ++k) ch = std::max(ch, cbeg[k + 1] - cbeg[k]);
         DevBuf<int32_t> c32;                       // the weight kernels write the pattern too; here it is the stencil array itself
         DevBuf<double> vb;                         // every chunk has its own slice: the solve never waits for a copy
+        DevBuf<int> dflags;                        // status words of every chunk, inspected once at the end
         CUDA_TRY(ctx, c32.alloc((size_t)ch * n, st));
         CUDA_TRY(ctx, vb.alloc((size_t)M * n * nops, st));
-        i32_to_i64_kernel<<<ceil_div_i64(N * n, 256), 256, 0, st>>>(stencils.p, N * n, opts->index_base, c64.p);
+        CUDA_TRY(ctx, dflags.alloc(8 * nchunks, st));
+        init_deferred_kernel<<<1, 8 * nchunks, 0, st>>>(dflags.p);
         KLAUNCH(ctx);
-        CUDA_TRY(ctx, cudaEventRecord(ctx->chunk_ev[2], st));
-        CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->chunk_ev[2], 0));
-        CUDA_TRY(ctx, cudaMemcpyAsync(colind_out, c64.p, sizeof(int64_t) * N * n, cudaMemcpyDeviceToHost, ctx->copy_stream));
+        // The pattern crosses PCIe as int32 (half the bytes of the caller's int64) into a pinned staging buffer, slice by
+        // slice; host threads widen every slice into colind_out as soon as its copy has landed, under the value copies.
+        // RBFFD_HOST_WIDEN=0 (or fewer than 8 hardware threads per local rank) widens on the device and ships int64.
+        const char* hw_env = getenv("RBFFD_HOST_WIDEN");
+        const char* wt_env = getenv("RBFFD_WIDEN_THREADS");
+        const char* lw_env = getenv("LOCAL_WORLD_SIZE");            // one process per GPU: share the host cores
+        const unsigned hc = std::thread::hardware_concurrency();
+        const unsigned lw = lw_env ? (unsigned)std::max(1, atoi(lw_env)) : 1u;
+        const int T = wt_env ? std::max(1, atoi(wt_env)) : (int)std::min(8u, hc / (2 * lw));
+        const bool host_widen = hw_env ? atoi(hw_env) != 0 : T >= 4;
+        constexpr int NSL = 8;
+        struct Wideners {                          // joined on every exit path (the threads only wait for queued copies)
+            std::vector<std::thread> th;
+            cudaEvent_t ev[NSL] = {};
+            std::vector<cudaEvent_t> chunk_done;
+            void finish() {
+                for (auto& t : th) if (t.joinable()) t.join();
+                th.clear();
+                for (int k = 0; k < NSL; ++k) if (ev[k]) { cudaEventDestroy(ev[k]); ev[k] = nullptr; }
+                for (auto e : chunk_done) cudaEventDestroy(e);
+                chunk_done.clear();
+            }
+            ~Wideners() { finish(); }
+        } wd;
+        std::vector<std::thread>& wideners = wd.th;
+        cudaEvent_t* sl_ev = wd.ev;
+        const int64_t total = N * (int64_t)n;
+        if (host_widen) {
+            if (ctx->stage_i32_count < (size_t)total) {
+                if (ctx->stage_i32) cudaFreeHost(ctx->stage_i32);
+                ctx->stage_i32 = nullptr; ctx->stage_i32_count = 0;
+                CUDA_TRY(ctx, cudaHostAlloc(&ctx->stage_i32, sizeof(int32_t) * (size_t)total, cudaHostAllocDefault));
+                ctx->stage_i32_count = (size_t)total;
+            }
+            CUDA_TRY(ctx, cudaEventRecord(ctx->chunk_ev[2], st));
+            CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->chunk_ev[2], 0));
+            const int64_t sl = ((total + NSL - 1) / NSL + 63) / 64 * 64;
+            for (int k = 0; k < NSL; ++k) {
+                const int64_t b0 = std::min<int64_t>(total, k * sl), b1 = std::min<int64_t>(total, b0 + sl);
+                CUDA_TRY(ctx, cudaEventCreateWithFlags(&sl_ev[k], cudaEventDisableTiming | cudaEventBlockingSync));
+                if (b1 > b0) CUDA_TRY(ctx, cudaMemcpyAsync(ctx->stage_i32 + b0, stencils.p + b0, sizeof(int32_t) * (b1 - b0), cudaMemcpyDeviceToHost, ctx->copy_stream));
+                CUDA_TRY(ctx, cudaEventRecord(sl_ev[k], ctx->copy_stream));
+            }
+            const int32_t* src = ctx->stage_i32;
+            const int64_t base = opts->index_base;
+            const int dev = ctx->device;
+            for (int t = 0; t < T; ++t)
+                wideners.emplace_back([=]() {
+                    cudaSetDevice(dev);
+                    for (int k = 0; k < NSL; ++k) {
+                        const int64_t b0 = std::min<int64_t>(total, k * sl), b1 = std::min<int64_t>(total, b0 + sl);
+                        cudaEventSynchronize(sl_ev[k]);
+                        const int64_t len = b1 - b0, per = (len + T - 1) / T;
+                        const int64_t e0 = b0 + std::min<int64_t>(len, t * per), e1 = b0 + std::min<int64_t>(len, (t + 1) * per);
+                        // streaming stores: the int64 pattern is written once and not read here (no read-for-ownership)
+                        for (int64_t e = e0; e < e1; ++e) _mm_stream_si64(reinterpret_cast<long long*>(colind_out + e), (long long)src[e] + base);
+                    }
+                    _mm_sfence();
+                });
+        } else {
+            CUDA_TRY(ctx, c64.alloc((size_t)N * n, st));
+            i32_to_i64_kernel<<<ceil_div_i64(N * n, 256), 256, 0, st>>>(stencils.p, N * n, opts->index_base, c64.p);
+            KLAUNCH(ctx);
+            CUDA_TRY(ctx, cudaEventRecord(ctx->chunk_ev[2], st));
+            CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->chunk_ev[2], 0));
+            CUDA_TRY(ctx, cudaMemcpyAsync(colind_out, c64.p, sizeof(int64_t) * N * n, cudaMemcpyDeviceToHost, ctx->copy_stream));
+        }
         lap("search + colind D2H queued");
         double t_weights = 0.0;
         int rc = RBFFD_OK;
-        int c = 0;
         ctx->trusted_stencils = true;              // produced by our own search: no range check per chunk
-        for (int64_t r0 = 0; r0 < M && rc == RBFFD_OK; r0 += ch, ++c) {
-            const int64_t cnt = std::min<int64_t>(ch, M - r0);
-            double* vchunk = vb.p + (size_t)r0 * n * nops;
-            rc = rbffd_weights_impl(ctx, opts, dX.p, N, dX.p + r0 * dim, cnt, stencils.p + r0 * n, cnt, nullptr, c32.p, vchunk);
-            t_weights += ctx->timings[3];
+        ctx->deferred_flags = dflags.p;            // no host synchronisation per chunk: the kernels queue back to back
+        struct Restore { rbffd_context* c; ~Restore() { c->deferred_flags = nullptr; c->trusted_stencils = false; } } restore{ctx};
+        std::vector<cudaEvent_t>& cev = wd.chunk_done;
+        CUDA_TRY(ctx, cudaEventRecord(ctx->ev[0], st));
+        auto ship = [&](int k) -> cudaError_t {    // values of chunk k -> host, on the copy stream
+            const int64_t r0 = cbeg[k], cnt = cbeg[k + 1] - r0;
+            const double* vchunk = vb.p + (size_t)r0 * n * nops;
+            for (int o = 0; o < nops; ++o) {
+                cudaError_t ce = cudaMemcpyAsync(vals_out + ((size_t)o * M + r0) * n, vchunk + (size_t)o * cnt * n, sizeof(double) * cnt * n,
+                                                 cudaMemcpyDeviceToHost, ctx->copy_stream);
+                if (ce != cudaSuccess) return ce;
+            }
+            return cudaSuccess;
+        };
+        for (int k = 0; k < nchunks && rc == RBFFD_OK; ++k) {
+            const int64_t r0 = cbeg[k], cnt = cbeg[k + 1] - r0;
+            if (cnt <= 0) continue;
+            ctx->deferred_slot = k;
+            rc = rbffd_weights_impl(ctx, opts, dX.p, N, dX.p + r0 * dim, cnt, stencils.p + r0 * n, cnt, nullptr, c32.p,
+                                    vb.p + (size_t)r0 * n * nops);
             if (rc != RBFFD_OK) break;
-            // weights_impl has synchronised `st`: chunk c is complete; ship it on the copy stream
-            for (int o = 0; o < nops; ++o)
-                CUDA_TRY(ctx, cudaMemcpyAsync(vals_out + ((size_t)o * M + r0) * n, vchunk + (size_t)o * cnt * n, sizeof(double) * cnt * n,
-                                              cudaMemcpyDeviceToHost, ctx->copy_stream));
-            lap("chunk solved");
+            cudaEvent_t ev;
+            CUDA_TRY(ctx, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+            cev.push_back(ev);
+            CUDA_TRY(ctx, cudaEventRecord(ev, st));
+            CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->copy_stream, ev, 0));
+            CUDA_TRY(ctx, ship(k));
+        }
+        CUDA_TRY(ctx, cudaEventRecord(ctx->ev[1], st));
+        lap("all chunks queued");
+        ctx->deferred_flags = nullptr;
+        int hf[2 * nchunks];
+        if (rc == RBFFD_OK) {
+            DevBuf<int> packed;
+            CUDA_TRY(ctx, packed.alloc(2 * nchunks, st));
+            pack_deferred_kernel<<<1, 32, 0, st>>>(dflags.p, nchunks, packed.p);
+            KLAUNCH(ctx);
+            CUDA_TRY(ctx, rbffd_fetch_flags(ctx, packed.p, 2 * nchunks, hf));     // synchronises `st`: every chunk is solved
+            lap("all chunks solved");
+            float ms = 0.f;
+            CUDA_TRY(ctx, cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]));
+            t_weights = ms;
+            for (int k = 0; k < nchunks && rc == RBFFD_OK; ++k) {
+                if (hf[2 * k] == 0x7fffffff && hf[2 * k + 1] == 0) continue;
+                // a stencil of this chunk was refused by the null-space kernel (or is singular): redo the chunk through the
+                // synchronous path, which falls back to the pivoted kernels and reports singular nodes
+                const int64_t r0 = cbeg[k], cnt = cbeg[k + 1] - r0;
+                rc = rbffd_weights_impl(ctx, opts, dX.p, N, dX.p + r0 * dim, cnt, stencils.p + r0 * n, cnt, nullptr, c32.p,
+                                        vb.p + (size_t)r0 * n * nops);
+                if (rc != RBFFD_OK) break;
+                CUDA_TRY(ctx, cudaEventRecord(ctx->chunk_ev[3], st));
+                CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->chunk_ev[3], 0));
+                CUDA_TRY(ctx, ship(k));
+            }
         }
         ctx->trusted_stencils = false;
         cudaError_t e = cudaStreamSynchronize(ctx->copy_stream);
         lap("copies drained");
+        wd.finish();
+        lap("pattern widened");
+        if (trace) fprintf(stderr, "[rbffd trace] weight kernels (device time, all chunks) %8.3f ms\n", t_weights);
         ctx->timings[3] = t_weights;
         // the stream-ordered temporaries are freed on `st`: make sure the copy stream is done with them first
         if (rc != RBFFD_OK) return rc;

@@ -24,6 +24,13 @@ struct rbffd_context {
     int* hflags_dev = nullptr;   // tiny kernel, never by a D2H memcpy (that would queue behind bulk D2H traffic on the copy engine)
     bool trusted_stencils = false;   // set by internal callers whose stencils come from our own search (skips range checks)
     long long launches = 0;      // hand-written kernels launched through this context (rbffd_launch_count)
+    // deferred status checks (host entry point): when set, the weight path writes its status words of the current row
+    // chunk to deferred_flags[8 * deferred_slot ..] ([0] singular node + 1, [4] null-space kernel refused) and never
+    // synchronises; the caller inspects all chunks once at the end and redoes the rare chunk that needs the fallback
+    int* deferred_flags = nullptr;
+    int deferred_slot = 0;
+    int32_t* stage_i32 = nullptr;    // pinned staging for the int32 pattern (host entry point widens it to the caller's int64)
+    size_t stage_i32_count = 0;
 };
 
 struct rbffd_operator {

@@ -433,9 +433,14 @@ int rbffd_weights_impl(rbffd_context* ctx, const rbffd_options* opts, const doub
     if (!Y) Y = X;
 
     DevBuf<int> flags;   // [0] singular node+1, [1] centre != identity, [2] bad index
-    CUDA_TRY(ctx, flags.alloc(4, st));
     int h_flags[4] = {0x7fffffff, 0, 0, 0};
-    rbffd_set_flags_kernel<<<1, 32, 0, st>>>(flags.p, h_flags[0], h_flags[1], h_flags[2], h_flags[3]);
+    const bool deferred = ctx->deferred_flags != nullptr && ctx->trusted_stencils && !center;
+    if (deferred) flags.p = ctx->deferred_flags + 8 * ctx->deferred_slot;     // initialised by the caller, never fetched here
+    else {
+        CUDA_TRY(ctx, flags.alloc(4, st));
+        rbffd_set_flags_kernel<<<1, 32, 0, st>>>(flags.p, h_flags[0], h_flags[1], h_flags[2], h_flags[3]);
+    }
+    struct Unhook { DevBuf<int>& f; bool on; ~Unhook() { if (on) f.p = nullptr; } } unhook{flags, deferred};
     if (!ctx->trusted_stencils) {
         check_range_kernel<<<ceil_div_i64(N * T.n, 256), 256, 0, st>>>(stencils, N * T.n, (int)NX, flags.p + 2);
         KLAUNCH(ctx);
@@ -532,6 +537,7 @@ int rbffd_weights_impl(rbffd_context* ctx, const rbffd_options* opts, const doub
         CUDA_TRY(ctx, cudaGetLastError());
     }
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev[6], st));
+    if (deferred) return RBFFD_OK;
     CUDA_TRY(ctx, rbffd_fetch_flags(ctx, flags.p, 4, h_flags));
     float ms;
     CUDA_TRY(ctx, cudaEventElapsedTime(&ms, ctx->ev[4], ctx->ev[5]));

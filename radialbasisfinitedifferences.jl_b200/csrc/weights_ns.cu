@@ -519,16 +519,20 @@ int rbffd_weights_ns(rbffd_context* ctx, const OpTables& T, const double* X, int
         }
     }
     DevBuf<int> redo;
-    CUDA_TRY(ctx, redo.alloc(1, ctx->stream));
-    CUDA_TRY(ctx, cudaMemsetAsync(redo.p, 0, sizeof(int), ctx->stream));
-    a.redo = redo.p;
+    const bool deferred = ctx->deferred_flags != nullptr;
+    if (deferred) a.redo = ctx->deferred_flags + 8 * ctx->deferred_slot + 4;
+    else {
+        CUDA_TRY(ctx, redo.alloc(1, ctx->stream));
+        CUDA_TRY(ctx, cudaMemsetAsync(redo.p, 0, sizeof(int), ctx->stream));
+        a.redo = redo.p;
+    }
     int rc = RBFFD_ERR_UNSUPPORTED;
     if (T.dim == 2 && T.q == 3 && table_matches<2, 3>(T)) rc = launch_ns<2, 3>(ctx, a);
     else if (T.dim == 2 && T.q == 6 && table_matches<2, 6>(T)) rc = launch_ns<2, 6>(ctx, a);
     else if (T.dim == 2 && T.q == 10 && table_matches<2, 10>(T)) rc = launch_ns<2, 10>(ctx, a);
     else if (T.dim == 3 && T.q == 4 && table_matches<3, 4>(T)) rc = launch_ns<3, 4>(ctx, a);
     else if (T.dim == 3 && T.q == 10 && table_matches<3, 10>(T)) rc = launch_ns<3, 10>(ctx, a);
-    if (rc != RBFFD_OK) return rc;
+    if (rc != RBFFD_OK || deferred) return rc;
     int h_redo = 0;
     CUDA_TRY(ctx, rbffd_fetch_flags(ctx, redo.p, 1, &h_redo));
     return h_redo ? RBFFD_ERR_UNSUPPORTED : RBFFD_OK;

@@ -155,6 +155,14 @@ __device__ __forceinline__ int gj_panel48(const double* __restrict__ Pbuf, doubl
     return bad;
 }
 
+#ifdef NSW_TIMING
+// development aid (make EXTRA=-DNSW_TIMING): wall cycles per phase, summed over stencils (thread 0 of warps 0 and 2)
+__device__ unsigned long long nsw_prof[16];
+#define NSW_T(slot, cond) do { if (cond) { const long long _t = clock64(); atomicAdd(&nsw_prof[slot], (unsigned long long)(_t - tprev)); tprev = _t; } } while (0)
+#else
+#define NSW_T(slot, cond) do { } while (0)
+#endif
+
 constexpr int WN_LD = 65;      // row stride of Phi (original stencil order)
 constexpr int WN_NBP = 48;     // padded null-space dimension (6 tiles)
 
@@ -209,6 +217,9 @@ __global__ void __launch_bounds__(128, 4) weights_nsw_kernel(WNArgs a) {
 
     for (int64_t i = blockIdx.x; i < a.NS; i += gridDim.x) {
         // ---- 0. scalestencil.jl:10-20: every warp reduces the whole stencil (identical s in all warps) ----
+#ifdef NSW_TIMING
+        long long tprev = clock64();
+#endif
         const int32_t* st = a.stencils + (a.center ? (int64_t)a.center[i] : i) * n;
         const int id0 = st[lane < n ? lane : 0], id1 = st[lane + 32 < n ? lane + 32 : 0];
         double sx[D], s[D], eta[D];
@@ -225,6 +236,8 @@ __global__ void __launch_bounds__(128, 4) weights_nsw_kernel(WNArgs a) {
         }
         unsigned kmin = 0xffffffffu;
         int bad = 0;
+        NSW_T(0, tid == 0);
+        NSW_T(9, tid == 64);
         if (warp < 2) {
             // ---- A1. column reduction of [P; g']: thread L2 < n holds row L2 of P, thread n + o the row g_o' ----
             double prow[Q];
@@ -304,6 +317,7 @@ __global__ void __launch_bounds__(128, 4) weights_nsw_kernel(WNArgs a) {
 #pragma unroll
                 for (int c = 0; c < QP; c += 2) dst[c >> 1] = make_double2(c < Q ? prow[c] : 0.0, c + 1 < Q ? prow[c + 1] : 0.0);
             }
+            NSW_T(1, tid == 0);
         } else {
             // ---- A2. Phi in original stencil order by symmetric pairs (round k pairs node l with (l + k) mod n), and
             //          the RBF part of the right-hand sides (generate_operator.jl:123-154) ----
@@ -328,8 +342,11 @@ __global__ void __launch_bounds__(128, 4) weights_nsw_kernel(WNArgs a) {
             }
             bar_named(2, 64);
             phs_assemble<D, DP, LD>(Sc, G, sx, l, n, L2 < n, hp);
+            NSW_T(2, tid == 64);
         }
         __syncthreads();
+        NSW_T(3, tid == 0);
+        NSW_T(4, tid == 64);
         // ---- B. Y = Phi~[:, N] - Phi~[:, B] W : row tiles 2*warp, 2*warp+1; permutation applied while gathering ----
         {
             double cy[2][NJ][2];
@@ -373,6 +390,7 @@ __global__ void __launch_bounds__(128, 4) weights_nsw_kernel(WNArgs a) {
                     *reinterpret_cast<double2*>(Yb + (8 * (2 * warp + ii) + g) * US + 8 * J + 2 * t) = make_double2(cy[ii][J][0], cy[ii][J][1]);
         }
         __syncthreads();
+        NSW_T(5, tid == 0);
         // ---- C. [S | t] = Y[N, :] - W' Y[B, :] : this warp owns tile columns warp and warp + 4 ----
         double c[6][2][2];
         const bool has2 = warp + 4 < NJ;
@@ -420,6 +438,7 @@ __global__ void __launch_bounds__(128, 4) weights_nsw_kernel(WNArgs a) {
             }
         }
         __syncthreads();                                  // the Y tile is dead: its storage becomes the exchange buffers
+        NSW_T(6, tid == 0);
         // ---- D. blocked Gauss-Jordan WITHOUT pivoting on the definite S (static pivot rows 4kb .. 4kb+3), with one
         //         step of lookahead: in step kb the owner of panel kb+1 updates that tile column first and eliminates the
         //         next panel while the other warps are still applying update kb ----
@@ -488,7 +507,8 @@ __global__ void __launch_bounds__(128, 4) weights_nsw_kernel(WNArgs a) {
             (([&] { if (4 * KB < nb) gj_step(std::integral_constant<int, KB>{}); }()), ...);
         }(std::make_integer_sequence<int, 12>{});
         if (bad < 0 || kmin < 64u) *a.redo = 1;
-        __syncthreads();                                  // every pivot reciprocal is published; Bt is dead (Ys aliases it)
+        __syncthreads();
+        NSW_T(7, tid == 0);                                  // every pivot reciprocal is published; Bt is dead (Ys aliases it)
         // y = RHS_row / pivot_row  (right-hand-side column rcb + o lives in tile (rcb + o) / 8)
 #pragma unroll
         for (int jj = 0; jj < 2; ++jj) {
@@ -536,6 +556,7 @@ __global__ void __launch_bounds__(128, 4) weights_nsw_kernel(WNArgs a) {
             }
         }
         __syncthreads();
+        NSW_T(8, tid == 0);
     }
 }
 
@@ -556,9 +577,20 @@ int launch_nsw2(rbffd_context* ctx, WNArgs& a) {
     CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int per_sm = std::max<int>(1, std::min<int>(4, (int)((228 * 1024) / (smem + 1024))));
     const int grid = (int)std::min<int64_t>(a.NS, (int64_t)ctx->sm_count * per_sm * 4);
+#ifdef NSW_TIMING
+    unsigned long long zero[16] = {};
+    cudaMemcpyToSymbolAsync(nsw_prof, zero, sizeof(zero), 0, cudaMemcpyHostToDevice, ctx->stream);
+#endif
     kern<<<grid, 128, smem, ctx->stream>>>(a);
     KLAUNCH(ctx);
     CUDA_TRY(ctx, cudaGetLastError());
+#ifdef NSW_TIMING
+    unsigned long long h[16];
+    cudaMemcpyFromSymbol(h, nsw_prof, sizeof(h));
+    static const char* nm[9] = {"0 load+scale", "A1 P reduction (warp 0)", "A2 Phi+rhs (warp 2)", "A wait (warp 0)", "A wait (warp 2)", "B Y",
+                                "C S", "D elimination", "E back+store"};
+    for (int k = 0; k < 9; ++k) fprintf(stderr, "[nsw timing] %-26s %9.0f cycles/stencil\n", nm[k], (double)h[k] / (double)a.NS);
+#endif
     return RBFFD_OK;
 }
 
@@ -607,16 +639,20 @@ int rbffd_weights_nsw(rbffd_context* ctx, const OpTables& T, const double* X, in
         }
     }
     DevBuf<int> redo;
-    CUDA_TRY(ctx, redo.alloc(1, ctx->stream));
-    CUDA_TRY(ctx, cudaMemsetAsync(redo.p, 0, sizeof(int), ctx->stream));
-    a.redo = redo.p;
+    const bool deferred = ctx->deferred_flags != nullptr;
+    if (deferred) a.redo = ctx->deferred_flags + 8 * ctx->deferred_slot + 4;
+    else {
+        CUDA_TRY(ctx, redo.alloc(1, ctx->stream));
+        CUDA_TRY(ctx, cudaMemsetAsync(redo.p, 0, sizeof(int), ctx->stream));
+        a.redo = redo.p;
+    }
     int rc = RBFFD_ERR_UNSUPPORTED;
     if (T.dim == 2 && T.q == 10) rc = launch_nsw<2, 10>(ctx, a);
     else if (T.dim == 2 && T.q == 15) rc = launch_nsw<2, 15>(ctx, a);
     else if (T.dim == 2 && T.q == 21) rc = launch_nsw<2, 21>(ctx, a);
     else if (T.dim == 3 && T.q == 10) rc = launch_nsw<3, 10>(ctx, a);
     else if (T.dim == 3 && T.q == 20) rc = launch_nsw<3, 20>(ctx, a);
-    if (rc != RBFFD_OK) return rc;
+    if (rc != RBFFD_OK || deferred) return rc;
     int h_redo = 0;
     CUDA_TRY(ctx, rbffd_fetch_flags(ctx, redo.p, 1, &h_redo));
     return h_redo ? RBFFD_ERR_UNSUPPORTED : RBFFD_OK;

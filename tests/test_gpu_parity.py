@@ -473,6 +473,48 @@ def test_chunked_host_path_with_pinned_buffers(ctx):
                                                    ctypes.c_void_p(ch.data_ptr()), ctypes.c_void_p(vh.data_ptr())))
     assert np.array_equal(ch.numpy(), col_ref)
     assert np.array_equal(vh.numpy(), val_ref)
+    # both ways of producing the caller's int64 pattern (int32 over PCIe + host threads / int64 widened on the device), 1-based
+    import os
+    opts1 = rb.make_options(2, 5, n, 3, ops, 1)
+    for mode in ("1", "0"):
+        os.environ["RBFFD_HOST_WIDEN"] = mode
+        try:
+            ch.zero_(); vh.zero_()
+            ctx._check(ctx._L.rbffd_generate_operator_host(ctx._h, ctypes.byref(opts1), ctypes.c_void_p(Xh.data_ptr()), N, None, N, None,
+                                                           ctypes.c_void_p(ch.data_ptr()), ctypes.c_void_p(vh.data_ptr())))
+        finally:
+            del os.environ["RBFFD_HOST_WIDEN"]
+        assert np.array_equal(ch.numpy(), col_ref + 1)
+        assert np.array_equal(vh.numpy(), val_ref)
+
+
+def test_chunked_host_path_deferred_status(ctx, oracle):
+    """The chunked host path queues every row chunk without a host synchronisation and inspects the status words once at the
+    end: a chunk whose stencils the null-space kernel refuses is redone by the pivoted kernels (same weights as the
+    synchronous path), and a singular stencil still surfaces as RBFFD_ERR_SINGULAR with its node index."""
+    import ctypes
+    import torch
+    X = rb.nodes.jittered_lattice(2, 60, seed=22)
+    N, n = len(X), 20
+    Xd = X.copy()
+    Xd[N - 7] = Xd[N - 8]                                   # duplicate node in the LAST chunk: singular interpolation matrix
+    opts = rb.make_options(2, 3, n, 3, ["Lap"])
+    Xh = torch.from_numpy(Xd).pin_memory()
+    ch = torch.empty((N, n), dtype=torch.int64).pin_memory()
+    vh = torch.empty((1, N, n), dtype=torch.float64).pin_memory()
+    rc = ctx._L.rbffd_generate_operator_host(ctx._h, ctypes.byref(opts), ctypes.c_void_p(Xh.data_ptr()), N, None, N, None,
+                                             ctypes.c_void_p(ch.data_ptr()), ctypes.c_void_p(vh.data_ptr()))
+    assert rc == rb._lib.ERR_SINGULAR
+    # nearly coincident nodes: the stencil is solvable but may fail the null-space kernel's checks; whatever path the chunk
+    # takes, the pinned and pageable entry points must agree bit for bit and stay within tolerance of the oracle
+    Xn = X.copy()
+    Xn[N // 2] = Xn[N // 2 + 1] + 1e-9
+    Xh.copy_(torch.from_numpy(Xn))
+    ctx._check(ctx._L.rbffd_generate_operator_host(ctx._h, ctypes.byref(opts), ctypes.c_void_p(Xh.data_ptr()), N, None, N, None,
+                                                   ctypes.c_void_p(ch.data_ptr()), ctypes.c_void_p(vh.data_ptr())))
+    col_ref, val_ref = rb.generate_raw(Xn, None, 3, n, 3, ["Lap"], ctx=ctx)
+    assert np.array_equal(ch.numpy(), col_ref)
+    assert np.array_equal(vh.numpy(), val_ref)
 
 
 def test_peer_memory_halo_exchange_two_gpus():

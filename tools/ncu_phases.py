@@ -6,19 +6,25 @@ rep, cubin, sub, srcf = sys.argv[1:5]
 NS = float(sys.argv[5]) if len(sys.argv) > 5 else 1e6
 top = int(sys.argv[6]) if len(sys.argv) > 6 else 30
 base_name = srcf.split("/")[-1]
-dis = subprocess.run(["nvdisasm", "-g", cubin], capture_output=True, text=True).stdout.splitlines()
+dis = subprocess.run(["nvdisasm", "-gi", cubin], capture_output=True, text=True).stdout.splitlines()
 start = [i for i, l in enumerate(dis) if l.startswith(".text.") and sub in l][0]
-line_of = {}; cur = None; last = None
+# -gi prints the whole inlining chain before an instruction (innermost first); the phase of an instruction is decided
+# by the OUTERMOST line that lies in the kernel's own source file
+line_of = {}; chain = []; cur = None; fresh = False
 for l in dis[start + 1:]:
-    if l.startswith("\t.section"): break
-    m = re.search(r'//## File "([^"]+)", line (\d+)(?: inlined at "([^"]+)", line (\d+))?', l)
+    if l.startswith("\t.section") or l.startswith(".text."): break
+    m = re.search(r'//## File "([^"]+)", line (\d+)', l)
     if m:
-        f = m.group(1).split("/")[-1]
-        if f == base_name: last = int(m.group(2))
-        elif m.group(3) and m.group(3).endswith(base_name): last = int(m.group(4))
-        cur = last; continue
+        if not fresh: chain = []; fresh = True
+        chain.append((m.group(1).split("/")[-1], int(m.group(2))))
+        continue
     m = re.match(r"\s+/\*([0-9a-f]{4,})\*/", l)
-    if m: line_of[int(m.group(1), 16)] = cur
+    if m:
+        if fresh:
+            own = [ln for f, ln in chain if f == base_name]
+            cur = own[-1] if own else cur
+            fresh = False
+        line_of[int(m.group(1), 16)] = cur
 out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(out)))
 hi = [i for i, r in enumerate(rows) if r and r[0] == "Address"][0]; hdr = rows[hi]
