@@ -314,6 +314,8 @@ def main():
 
     # ---- end to end through the reference-facing host call: pinned host X in, host CSR out, copies inside the timing
     if args.profile:
+        if rank == 0:
+            print(json.dumps({"profile_run": True, "ms_per_step": ms_per_step, "phases_ms": {k: v / K for k, v in phase.items()}}))
         if halo is not None:
             halo.close()
         if world > 1:

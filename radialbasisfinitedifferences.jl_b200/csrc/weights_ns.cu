@@ -69,8 +69,10 @@ __device__ __forceinline__ double warp_max_nonneg(double v) {
 }
 
 constexpr int NS_NB = 24;      // padded null-space dimension (3 tiles)
-constexpr int NS_LD = 33;      // row stride of the Phi tile
-constexpr int NS_US = 34;      // row stride of the Y / [S|t] exchange tile (even: 16-byte rows)
+// Row strides == 4 (mod 16) doubles: the symmetric pair stores of the assembly (addresses 37 l + k and 37 l + 36 k over the
+// lanes l), the DMMA fragment loads (36 g + t) and the Y_B fragment loads (36 t + g) are all free of bank conflicts.
+constexpr int NS_LD = 36;      // row stride of the Phi tile
+constexpr int NS_US = 36;      // row stride of the Y / [S|t] exchange tile (even: 16-byte rows)
 
 // graded monomials of build_op_tables (weights.cu): mono[t] = mono[mpar[t]] * x[maxis[t]]
 template <int D, int Q>
@@ -122,10 +124,19 @@ __global__ void __launch_bounds__(128, MINB) weights_ns_kernel(NArgs a) {
     const int go = gl ? lane - n : lane;              // operator whose g row this lane owns
     const bool gown = go >= 0 && go < nops;
 
-    for (int64_t i = blockIdx.x * 4ll + warp; i < a.NS; i += (int64_t)gridDim.x * 4) {
+    // node id of this lane in the stencil of row i; the ids of the NEXT row are fetched one iteration ahead and its
+    // coordinates are pulled into L1 under the elimination, so that phase 0 does not sit on two dependent DRAM round trips
+    auto stencil_id = [&](int64_t row) -> int {
+        const int32_t* st = a.stencils + (a.center ? (int64_t)a.center[row] : row) * n;
+        return st[lane < n ? lane : 0];
+    };
+    const int64_t istride = (int64_t)gridDim.x * 4;
+    int64_t i = blockIdx.x * 4ll + warp;
+    int id_next = i < a.NS ? stencil_id(i) : 0;
+    for (; i < a.NS; i += istride) {
         // ---- 0. scalestencil.jl:10-20: lane l owns stencil node l ----
-        const int32_t* st = a.stencils + (a.center ? (int64_t)a.center[i] : i) * n;
-        const int id = st[lane < n ? lane : 0];
+        const int id = id_next;
+        if (i + istride < a.NS) id_next = stencil_id(i + istride);
         double sx[D], s[D], eta[D];
         bool eta_zero = true;
 #pragma unroll
@@ -296,12 +307,14 @@ __global__ void __launch_bounds__(128, MINB) weights_ns_kernel(NArgs a) {
         }
         // ---- 5. [S | t] = Y[N, :] - W' Y[B, :] ----
         __syncwarp();                                     // Phi~ is dead: the Y tile reuses its storage
+        // only the rows of the basic nodes (Y_B, positions nb .. n-1) are read back; Y_N stays in the accumulators
 #pragma unroll
         for (int J = 0; J < 4; ++J)
             if (J < NJ) {
 #pragma unroll
                 for (int I = 0; I < 4; ++I)
-                    *reinterpret_cast<double2*>(Yb + (8 * I + g) * US + 8 * J + 2 * t) = make_double2(c[I][J][0], c[I][J][1]);
+                    if (8 * I + 8 > nb)
+                        *reinterpret_cast<double2*>(Yb + (8 * I + g) * US + 8 * J + 2 * t) = make_double2(c[I][J][0], c[I][J][1]);
             }
         __syncwarp();
 #pragma unroll
@@ -339,6 +352,10 @@ __global__ void __launch_bounds__(128, MINB) weights_ns_kernel(NArgs a) {
         }
         // ---- 6. blocked Gauss-Jordan WITHOUT pivoting on the definite S: the block step of weights_fast.cu with
         //         static pivot rows (row 4kb+s), so no pivot search, no row selects and a static pivot-row dump ----
+        if (i + istride < a.NS) {
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(a.X + (int64_t)id_next * D));
+            if (lane < D) asm volatile("prefetch.global.L1 [%0];" ::"l"(a.Y + (i + istride) * D + lane));
+        }
         constexpr int PS6 = 36, US6 = 36;                 // strides == 4 (mod 16): conflict-free fragment loads
         double* Pbuf = G;                                 // [4][PS6]   (the Y tile is dead)
         double* Lbuf = Pbuf + 4 * PS6;                    // [4][PS6]

@@ -163,14 +163,14 @@ __device__ unsigned long long nsw_prof[16];
 #define NSW_T(slot, cond) do { } while (0)
 #endif
 
-constexpr int WN_LD = 65;      // row stride of Phi (original stencil order)
+constexpr int WN_LD = 68;      // row stride of Phi (original stencil order); == 4 (mod 16): pair stores 69 l + k, 69 l + 68 k conflict-free
 constexpr int WN_NBP = 48;     // padded null-space dimension (6 tiles)
 
 template <int D, int Q, bool FOLD>
 struct WnCfg {
     static constexpr int KS = (Q + 3) / 4, QP = 4 * KS;
     static constexpr int NJ = FOLD ? 6 : 7;              // tile columns of [S | t]
-    static constexpr int US = 8 * NJ + 2;                // row stride of the Y tile (even: 16-byte rows)
+    static constexpr int US = ((8 * NJ + 15) & ~15) + 4;  // row stride of the Y tile, == 4 (mod 16): Y_B fragment loads 4 t + g conflict-free
     static constexpr int DP = D == 2 ? 2 : 4;
     static constexpr int CS = (Q + 2) & ~1;              // candidate row: Q entries + the reciprocal of the pivot, even
     // doubles
@@ -197,7 +197,8 @@ __global__ void __launch_bounds__(128, 4) weights_nsw_kernel(WNArgs a) {
     double* cand = Sc + C::SC;
     double* Bt = cand + C::CAND;                      // [64][BS] RBF right-hand sides, original order
     double* Ys = Bt;                                  // solution y, [op][48] (Bt is dead by then; 8*48 <= 64*BS needs BS >= 6 or nops <= BS)
-    unsigned* candkey = reinterpret_cast<unsigned*>(Bt + 64 * BS);     // [2][2]
+    double* pf = Bt + 64 * BS;                        // [8] chain-rule factor of every operator
+    unsigned* candkey = reinterpret_cast<unsigned*>(pf + 8);           // [2][2]
     int* perm = reinterpret_cast<int*>(candkey + 4);                   // [64] position -> original stencil slot
     int* cnt0 = perm + 64;                                             // non-basic rows held by warp 0
     const double EPS = 2.220446049250313e-16;
@@ -510,6 +511,7 @@ __global__ void __launch_bounds__(128, 4) weights_nsw_kernel(WNArgs a) {
         __syncthreads();
         NSW_T(7, tid == 0);                                  // every pivot reciprocal is published; Bt is dead (Ys aliases it)
         // y = RHS_row / pivot_row  (right-hand-side column rcb + o lives in tile (rcb + o) / 8)
+        if (tid < nops) pf[tid] = op_post_factor<D>(T, tid, s);
 #pragma unroll
         for (int jj = 0; jj < 2; ++jj) {
             const int J = warp + 4 * jj;
@@ -528,26 +530,44 @@ __global__ void __launch_bounds__(128, 4) weights_nsw_kernel(WNArgs a) {
         // ---- E. w[N] = y, w[B] = w_p - W y; rescale and scatter into the CSR row (generate_operator.jl:161-182) ----
         {
             bool fin = true;
-            for (int idx = tid; idx < n * nops; idx += 128) {
-                const int o = idx / n, pos = idx - o * n;
-                const double* yv = Ys + o * NBP;
-                double wv;
-                if (pos < nb) wv = yv[pos];
-                else {
-                    const int cc = pos - nb;
-                    double acc0 = Wt[(rcb + o) * QP + cc], acc1 = 0.0;
-                    const double* wcol = Wt + cc;
-                    int aa = 0;
-                    for (; aa + 1 < nb; aa += 2) {
-                        acc0 = fma(-wcol[aa * QP], yv[aa], acc0);
-                        acc1 = fma(-wcol[(aa + 1) * QP], yv[aa + 1], acc1);
-                    }
-                    if (aa < nb) acc0 = fma(-wcol[aa * QP], yv[aa], acc0);
-                    wv = acc0 + acc1;
-                }
-                wv *= op_post_factor<D>(T, o, s);
-                fin = fin && (fabs(wv) < __longlong_as_double(0x7ff0000000000000ll));   // a zero pivot shows up as a non-finite weight
+            const double INF = __longlong_as_double(0x7ff0000000000000ll);
+            // non-basic nodes: w = y
+            for (int idx = tid; idx < nb * nops; idx += 128) {
+                const int o = idx / nb, pos = idx - o * nb;
+                const double wv = Ys[o * NBP + pos] * pf[o];
+                fin = fin && (fabs(wv) < INF);              // a zero pivot shows up as a non-finite weight
                 a.vals[((int64_t)o * a.M + i) * n + perm[pos]] = wv;
+            }
+            // basic nodes: the Q x nops block  w_p - W' y  as one DMMA row tile per warp (rows = basic nodes 8 warp + g,
+            // columns = operators 2t, 2t+1, k = non-basic nodes)
+            if (8 * warp < Q) {
+                const int cc = 8 * warp + g;
+                const bool rin = cc < Q;
+                double c0 = (rin && 2 * t < nops) ? Wt[(rcb + 2 * t) * QP + (rin ? cc : 0)] : 0.0;
+                double c1 = (rin && 2 * t + 1 < nops) ? Wt[(rcb + 2 * t + 1) * QP + (rin ? cc : 0)] : 0.0;
+                const double* wcol = Wt + (rin ? cc : 0);
+                const double* ycol = Ys + (g < nops ? g : 0) * NBP;
+#pragma unroll 2
+                for (int k0 = 0; k0 < nb; k0 += 4) {
+                    const int aa = k0 + t;
+                    const bool kin = aa < nb;
+                    const double af = (rin && kin) ? -wcol[(kin ? aa : 0) * QP] : 0.0;
+                    const double bf = (g < nops && kin) ? ycol[kin ? aa : 0] : 0.0;
+                    dmma884w(c0, c1, af, bf);
+                }
+                if (rin) {
+                    const int dst = perm[nb + cc];
+                    if (2 * t < nops) {
+                        const double wv = c0 * pf[2 * t];
+                        fin = fin && (fabs(wv) < INF);
+                        a.vals[((int64_t)(2 * t) * a.M + i) * n + dst] = wv;
+                    }
+                    if (2 * t + 1 < nops) {
+                        const double wv = c1 * pf[2 * t + 1];
+                        fin = fin && (fabs(wv) < INF);
+                        a.vals[((int64_t)(2 * t + 1) * a.M + i) * n + dst] = wv;
+                    }
+                }
             }
             if (!fin) *a.redo = 1;
             if (warp == 0) {
@@ -571,7 +591,7 @@ template <int D, int Q, bool FOLD>
 int launch_nsw2(rbffd_context* ctx, WNArgs& a) {
     using C = WnCfg<D, Q, FOLD>;
     a.bs = std::max(6, (a.T.nops + 1) & ~1);             // Ys [nops][48] aliases Bt [64][bs]
-    const size_t smem = ((size_t)(C::G + C::WT + C::SC + C::CAND + 64 * a.bs) * 8 + 4 * 4 + 64 * 4 + 16 + 15) & ~(size_t)15;
+    const size_t smem = ((size_t)(C::G + C::WT + C::SC + C::CAND + 64 * a.bs + 8) * 8 + 4 * 4 + 64 * 4 + 16 + 15) & ~(size_t)15;
     if ((int64_t)smem > ctx->max_smem_optin) return RBFFD_ERR_UNSUPPORTED;
     auto kern = weights_nsw_kernel<D, Q, FOLD>;
     CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
