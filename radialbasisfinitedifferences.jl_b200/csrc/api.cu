@@ -289,7 +289,7 @@ int rbffd_generate_operator_host(rbffd_context* ctx, const rbffd_options* opts, 
     const bool pinned = cudaPointerGetAttributes(&pa_c, colind_out) == cudaSuccess && pa_c.type == cudaMemoryTypeHost &&
                         cudaPointerGetAttributes(&pa_v, vals_out) == cudaSuccess && pa_v.type == cudaMemoryTypeHost;
     cudaGetLastError();
-    const int nchunks = 8;
+    const int nchunks = 5;
     if (pinned && Y == X && M == N && M >= 64 * nchunks && !opts->sort_columns) {
         const bool trace = getenv("RBFFD_TRACE") != nullptr;
         const auto t_begin = std::chrono::steady_clock::now();
@@ -307,7 +307,7 @@ int rbffd_generate_operator_host(rbffd_context* ctx, const rbffd_options* opts, 
         // chunk is the only one that nothing overlaps).
         int64_t cbeg[nchunks + 1];
         {
-            static const double frac[nchunks] = {0.30, 0.24, 0.17, 0.12, 0.08, 0.05, 0.025, 0.015};
+            static const double frac[nchunks] = {0.38, 0.28, 0.18, 0.11, 0.05};
             double acc = 0.0;
             cbeg[0] = 0;
             for (int k = 0; k < nchunks; ++k) {
