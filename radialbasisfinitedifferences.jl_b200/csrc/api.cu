@@ -400,7 +400,9 @@ int rbffd_generate_operator_host(rbffd_context* ctx, const rbffd_options* opts, 
         struct Restore { rbffd_context* c; ~Restore() { c->deferred_flags = nullptr; c->trusted_stencils = false; } } restore{ctx};
         std::vector<cudaEvent_t>& cev = wd.chunk_done;
         CUDA_TRY(ctx, cudaEventRecord(ctx->ev[0], st));
+        const bool dbg_noship = getenv("RBFFD_DEBUG_NOSHIP") != nullptr;     // timing experiments only: results stay on the device
         auto ship = [&](int k) -> cudaError_t {    // values of chunk k -> host, on the copy stream
+            if (dbg_noship) return cudaSuccess;
             const int64_t r0 = cbeg[k], cnt = cbeg[k + 1] - r0;
             const double* vchunk = vb.p + (size_t)r0 * n * nops;
             for (int o = 0; o < nops; ++o) {
