@@ -334,7 +334,9 @@ int rbffd_generate_operator_host(rbffd_context* ctx, const rbffd_options* opts, 
         const unsigned hc = std::thread::hardware_concurrency();
         const unsigned lw = lw_env ? (unsigned)std::max(1, atoi(lw_env)) : 1u;
         const int T = wt_env ? std::max(1, atoi(wt_env)) : (int)std::min(8u, hc / (2 * lw));
-        const bool host_widen = hw_env ? atoi(hw_env) != 0 : T >= 4;
+        // several ranks on one host: PCIe writes of all GPUs plus the widening traffic contend for host memory bandwidth
+        // (measured at N = 2: 11.1 ms per call with host widening), so the default there is the device-side widening
+        const bool host_widen = hw_env ? atoi(hw_env) != 0 : (lw == 1 && T >= 4);
         constexpr int NSL = 8;
         struct Wideners {                          // joined on every exit path (the threads only wait for queued copies)
             std::vector<std::thread> th;
