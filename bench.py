@@ -381,7 +381,7 @@ def main():
                        "l2": "every step writes %.0f MB of stencils+operator (> 126 MB L2), so no input survives in L2 between steps" % ((M * n * 4 * 2 + r * M * n * 8) / 1e6),
                        "parallelism": "slab x%d, halo_rows=%d, halo exchange: %s" % (world, halo_rows, "none" if world == 1 else ("NVLink peer-memory stores (CUDA IPC)" if use_p2p else "NCCL send/recv")), "global_nodes": total_nodes},
             "phases_ms": {"knn": phase["knn"] / K, "weights": phase["weights"] / K, "spmv(+halo)": phase["spmv"] / K},
-            "roofline": {"kernel": "weights (fused assemble + pivoted LU + solve + CSR write)", "bound": "fp64",
+            "roofline": {"kernel": "fused weight kernel (assemble + null-space elimination + solve + CSR write), flops by the LU convention (2/3)m^3 + 2m^2 r", "bound": "fp64",
                          "achieved": ach_w, "peak": fp64_peak, "unit": "TFLOP/s", "frac": ach_w / fp64_peak,
                          "flop_per_stencil": F, "traffic": traffic.get("weights"),
                          "peak_source": "measured live in this run by rbffd_measure_fp64_peak (DFMA %.2f / DMMA %.2f TFLOP/s burst); "

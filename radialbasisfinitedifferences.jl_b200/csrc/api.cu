@@ -336,7 +336,7 @@ int rbffd_generate_operator_host(rbffd_context* ctx, const rbffd_options* opts, 
         const int T = wt_env ? std::max(1, atoi(wt_env)) : (int)std::min(8u, hc / (2 * lw));
         // several ranks on one host: PCIe writes of all GPUs plus the widening traffic contend for host memory bandwidth
         // (measured at N = 2: 11.1 ms per call with host widening), so the default there is the device-side widening
-        const bool host_widen = hw_env ? atoi(hw_env) != 0 : (lw == 1 && T >= 4);
+        bool host_widen = hw_env ? atoi(hw_env) != 0 : (lw == 1 && T >= 4);
         constexpr int NSL = 8;
         struct Wideners {                          // joined on every exit path (the threads only wait for queued copies)
             std::vector<std::thread> th;
@@ -354,13 +354,13 @@ int rbffd_generate_operator_host(rbffd_context* ctx, const rbffd_options* opts, 
         std::vector<std::thread>& wideners = wd.th;
         cudaEvent_t* sl_ev = wd.ev;
         const int64_t total = N * (int64_t)n;
+        if (host_widen && ctx->stage_i32_count < (size_t)total) {
+            if (ctx->stage_i32) cudaFreeHost(ctx->stage_i32);
+            ctx->stage_i32 = nullptr; ctx->stage_i32_count = 0;
+            if (cudaHostAlloc(&ctx->stage_i32, sizeof(int32_t) * (size_t)total, cudaHostAllocDefault) == cudaSuccess) ctx->stage_i32_count = (size_t)total;
+            else { cudaGetLastError(); ctx->stage_i32 = nullptr; host_widen = false; }     // no pinned memory left: widen on the device
+        }
         if (host_widen) {
-            if (ctx->stage_i32_count < (size_t)total) {
-                if (ctx->stage_i32) cudaFreeHost(ctx->stage_i32);
-                ctx->stage_i32 = nullptr; ctx->stage_i32_count = 0;
-                CUDA_TRY(ctx, cudaHostAlloc(&ctx->stage_i32, sizeof(int32_t) * (size_t)total, cudaHostAllocDefault));
-                ctx->stage_i32_count = (size_t)total;
-            }
             CUDA_TRY(ctx, cudaEventRecord(ctx->chunk_ev[2], st));
             CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->chunk_ev[2], 0));
             const int64_t sl = ((total + NSL - 1) / NSL + 63) / 64 * 64;
