@@ -149,6 +149,11 @@ int rbffd_spmv_t_device(rbffd_operator* op, int32_t which, double alpha, const d
 /* y = sum_i coef[i] * D[which[i]] * x  in ONE pass over the shared pattern (fused multi-operator SpMV) */
 int rbffd_spmv_multi_device(rbffd_operator* op, int32_t nterms, const int32_t* which, const double* coef,
                             const double* x, double* y);
+/* vals_out[e] = sum_i coef[i] * D[which[i]].vals[e]  over the M*n entries of the shared pattern: the scalar-times-sparse
+ * and sparse-plus-sparse products of `alpha*D_xx + alpha*D_yy - u_x*D_x - u_y*D_y` (adv_diff_test.jl:151-152) done ONCE
+ * when the coefficients are constant, so that every right-hand-side evaluation is a single-matrix SpMV (12n + 16 B/row).
+ * vals_out: caller-owned device array of M*n doubles; wrap it with rbffd_operator_from_device(…, colind of op, vals_out). */
+int rbffd_operator_combine_device(rbffd_operator* op, int32_t nterms, const int32_t* which, const double* coef, double* vals_out);
 int rbffd_spmv_host(rbffd_operator* op, int32_t which, double alpha, const double* x, double beta, double* y);
 int rbffd_spmv_t_host(rbffd_operator* op, int32_t which, double alpha, const double* v, double beta, double* y);
 

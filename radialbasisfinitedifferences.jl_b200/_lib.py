@@ -81,6 +81,7 @@ _SIGNATURES = {
     "rbffd_spmv_device": ([_vp, _i32, _dbl, _vp, _dbl, _vp], C.c_int),
     "rbffd_spmv_t_device": ([_vp, _i32, _dbl, _vp, _dbl, _vp], C.c_int),
     "rbffd_spmv_multi_device": ([_vp, _i32, C.POINTER(_i32), C.POINTER(_dbl), _vp, _vp], C.c_int),
+    "rbffd_operator_combine_device": ([_vp, _i32, C.POINTER(_i32), C.POINTER(_dbl), _vp], C.c_int),
     "rbffd_spmv_host": ([_vp, _i32, _dbl, _vp, _dbl, _vp], C.c_int),
     "rbffd_spmv_t_host": ([_vp, _i32, _dbl, _vp, _dbl, _vp], C.c_int),
     "rbffd_rhs_advdiff_device": ([_vp, C.POINTER(AdvDiffParams), _vp, _vp], C.c_int),

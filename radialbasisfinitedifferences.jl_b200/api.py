@@ -240,6 +240,12 @@ class Operator:
         c = (C.c_double * len(coef))(*coef)
         self.ctx._check(self.ctx._L.rbffd_spmv_multi_device(self._h, len(which), w, c, x_ptr, y_ptr))
 
+    def combine_device(self, which, coef, vals_out_ptr):
+        """vals_out = sum_i coef[i] * D[which[i]] over the shared pattern (constant-coefficient alpha*Dxx + ... done once)"""
+        w = (C.c_int32 * len(which))(*which)
+        c = (C.c_double * len(coef))(*coef)
+        self.ctx._check(self.ctx._L.rbffd_operator_combine_device(self._h, len(which), w, c, vals_out_ptr))
+
     def rhs_advdiff_device(self, u_ptr, du_ptr, params: AdvDiffParams):
         self.ctx._check(self.ctx._L.rbffd_rhs_advdiff_device(self._h, C.byref(params), u_ptr, du_ptr))
 

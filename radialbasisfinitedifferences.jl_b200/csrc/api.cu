@@ -583,6 +583,50 @@ int rbffd_spmv_multi_device(rbffd_operator* op, int32_t nterms, const int32_t* w
     return rbffd_spmv_multi_impl(op, nterms, which, coef, x, 0.0, y);
 }
 
+namespace {
+struct CombineArgs { const double* v[8]; double c[8]; int nt; };
+__global__ void __launch_bounds__(256) combine_values_kernel(CombineArgs a, int64_t count, double* __restrict__ out, bool vec) {
+    const int64_t e = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) * 2;
+    if (vec && e + 1 < count) {                         // every base pointer is 16-byte aligned: 16-byte streaming loads
+        double2 acc = make_double2(0.0, 0.0);
+        for (int k = 0; k < a.nt; ++k) {
+            const double2 v = __ldcs(reinterpret_cast<const double2*>(a.v[k] + e));
+            acc.x = fma(a.c[k], v.x, acc.x);
+            acc.y = fma(a.c[k], v.y, acc.y);
+        }
+        *reinterpret_cast<double2*>(out + e) = acc;
+    } else {
+        for (int64_t f = e; f < count && f < e + 2; ++f) {
+            double acc = 0.0;
+            for (int k = 0; k < a.nt; ++k) acc = fma(a.c[k], a.v[k][f], acc);
+            out[f] = acc;
+        }
+    }
+}
+}  // namespace
+
+int rbffd_operator_combine_device(rbffd_operator* op, int32_t nterms, const int32_t* which, const double* coef, double* vals_out) {
+    if (!op) return RBFFD_ERR_INVALID;
+    rbffd_context* ctx = op->ctx;
+    if (nterms < 1 || nterms > 8 || !which || !coef || !vals_out) RBFFD_FAIL(ctx, RBFFD_ERR_INVALID, "operator_combine: 1..8 terms and non-NULL arrays");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    CombineArgs a;
+    a.nt = nterms;
+    const int64_t count = op->M * (int64_t)op->n;
+    for (int k = 0; k < nterms; ++k) {
+        if (which[k] < 0 || which[k] >= op->nmat) RBFFD_FAIL(ctx, RBFFD_ERR_INVALID, "operator_combine: matrix index %d out of range", which[k]);
+        a.v[k] = op->vals + (size_t)which[k] * count;
+        a.c[k] = coef[k];
+    }
+    if (count == 0) return RBFFD_OK;
+    bool vec = (reinterpret_cast<uintptr_t>(vals_out) & 15) == 0;
+    for (int k = 0; k < nterms; ++k) vec = vec && (reinterpret_cast<uintptr_t>(a.v[k]) & 15) == 0;
+    combine_values_kernel<<<ceil_div_i64((count + 1) / 2, 256), 256, 0, ctx->stream>>>(a, count, vals_out, vec);
+    KLAUNCH(ctx);
+    CUDA_TRY(ctx, cudaGetLastError());
+    return RBFFD_OK;
+}
+
 int rbffd_spmv_t_device(rbffd_operator* op, int32_t which, double alpha, const double* v, double beta, double* y) {
     if (!op) return RBFFD_ERR_INVALID;
     CUDA_TRY(op->ctx, cudaSetDevice(op->ctx->device));

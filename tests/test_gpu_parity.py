@@ -533,6 +533,35 @@ def test_peer_memory_halo_exchange_two_gpus():
     assert "OK" in r.stdout
 
 
+def test_operator_combine(ctx, oracle):
+    """rbffd_operator_combine_device: alpha*Lap - ux*Dx - uy*Dy as ONE value array over the shared pattern (the sparse sum the
+    reference forms inside every cons_sys call, adv_diff_test.jl:151-152); applying it equals the fused multi-operator SpMV."""
+    import torch
+    X = rb.nodes.jittered_lattice(2, 45, seed=12)
+    N, n = len(X), 30
+    colind, vals = rb.generate_raw(X, None, 5, n, 3, ["Lap", "Dx", "Dy"], ctx=ctx)
+    op = rb.Operator.from_host(ctx, colind, vals, N)
+    coef = [0.7, -1.3, 0.4]
+    vc = torch.empty((1, N, n), dtype=torch.float64, device="cuda")
+    op.combine_device([0, 1, 2], coef, vc.data_ptr())
+    ctx.synchronize()
+    ref = coef[0] * vals[0] + coef[1] * vals[1] + coef[2] * vals[2]
+    got = vc.cpu().numpy()[0]
+    assert np.max(np.abs(got - ref)) <= 4 * EPS * np.max(np.abs(coef[0] * vals[0]) + np.abs(coef[1] * vals[1]) + np.abs(coef[2] * vals[2]))
+    ci, _ = op.pointers(0)
+    opc = ctx.operator_from_device(N, N, n, 1, ci, vc.data_ptr())
+    u = torch.from_numpy(np.random.default_rng(1).standard_normal(N)).cuda()
+    y1 = torch.empty(N, dtype=torch.float64, device="cuda")
+    y2 = torch.empty(N, dtype=torch.float64, device="cuda")
+    opc.spmv_device(0, u.data_ptr(), y1.data_ptr())
+    op.spmv_multi_device([0, 1, 2], coef, u.data_ptr(), y2.data_ptr())
+    ctx.synchronize()
+    bound = oracle.spmv(colind, np.abs(ref), np.abs(u.cpu().numpy()))
+    assert np.all(np.abs((y1 - y2).cpu().numpy()) <= 1e-13 * bound + 1e-300)
+    with pytest.raises(rb.RbffdError):
+        op.combine_device([0, 5], [1.0, 1.0], vc.data_ptr())
+
+
 def _run_example_3d(nproc, g, steps):
     import json
     import os
