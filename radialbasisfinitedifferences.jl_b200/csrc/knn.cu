@@ -18,6 +18,7 @@
 #include <cfloat>
 #include <cmath>
 
+#include <cstdlib>
 #include "common.cuh"
 
 namespace {
@@ -360,7 +361,9 @@ int build_bins(rbffd_context* ctx, const double* X, int64_t N, int dim, int k_hi
     }
     // points per cell so that two rings of cells usually enclose the k-ball (kNN)
     const double unit_ball[4] = {1.0, 2.0, 3.141592653589793, 4.18879020478639};
-    double ppc = 1.15 * k_hint / (unit_ball[dim] * std::pow(2.0, dim));
+    // points per cell: two rings of cells usually enclose the k-ball; RBFFD_KNN_PPC rescales the default factor 1.15 (tuning knob)
+    static const double ppc_factor = [] { const char* e = getenv("RBFFD_KNN_PPC"); const double f = e ? atof(e) : 0.0; return f > 0.0 ? f : 1.15; }();
+    double ppc = ppc_factor * k_hint / (unit_ball[dim] * std::pow(2.0, dim));
     ppc = std::min(std::max(ppc, 1.0), 16.0);
     double h = 1.0;
     if (deff > 0) h = std::pow(vol * ppc / (double)N, 1.0 / deff);
