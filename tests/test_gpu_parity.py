@@ -457,6 +457,19 @@ def test_device_resident_time_stepping_example(oracle, mesh):
     assert np.allclose(u[np.array(idx_bc[0])], 1.0, atol=1e-2)
 
 
+def test_time_stepping_cuda_graph_replay():
+    """The SSP-RK3 step of the config 1 example captured once into a CUDA graph (the context launches on the capture stream)
+    and replayed: bit-identical fields to the eager loop."""
+    import importlib.util, os
+    spec = importlib.util.spec_from_file_location("adv_diff_b200", os.path.join(os.path.dirname(__file__), "..", "examples", "adv_diff_b200.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    path = os.path.join(os.path.dirname(__file__), "golden", "rect_0_10.cgns")
+    _, u_eager, _ = mod.run(steps=15, verbose=False, mesh=path)
+    _, u_graph, _ = mod.run(steps=15, verbose=False, mesh=path, graph=True)
+    assert np.array_equal(u_eager, u_graph)
+
+
 def test_chunked_host_path_with_pinned_buffers(ctx):
     """rbffd_generate_operator_host overlaps the D2H of finished row chunks with the next chunk's solve when the caller's
     output buffers are pinned; the result must be bit-identical to the one-shot path (pageable buffers)."""
