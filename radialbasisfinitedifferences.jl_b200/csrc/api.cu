@@ -538,7 +538,8 @@ int rbffd_operator_destroy(rbffd_operator* op) {
     if (!op) return RBFFD_OK;
     if (op->ctx) { cudaSetDevice(op->ctx->device); cudaStreamSynchronize(op->ctx->stream); }
     if (!op->borrowed) { cudaFree(op->colind); cudaFree(op->vals); }
-    cudaFree(op->t_ptr); cudaFree(op->t_src); cudaFree(op->work);
+    cudaFree(op->t_ptr); cudaFree(op->t_src); cudaFree(op->t_row); cudaFree(op->work);
+    for (double* p : op->t_vals) cudaFree(p);
     delete op;
     return RBFFD_OK;
 }

@@ -42,6 +42,9 @@ struct rbffd_operator {
     // lazily built transpose pattern (for E' * v): CSC of the M x N pattern
     int32_t* t_ptr = nullptr;    // [N+1]
     int32_t* t_src = nullptr;    // [M*n] entry id (k*n+j) sorted by column
+    int32_t* t_row = nullptr;    // [M*n] row of that entry (t_src / n)
+    std::vector<double*> t_vals; // [nmat] values in column order, built on the first E'*v of a matrix (owned operators only:
+                                 // a borrowed operator's values may be rewritten by the caller between applications)
     double* work = nullptr;      // [M] scratch
     bool borrowed = false;       // colind/vals belong to the caller (rbffd_operator_from_device)
 };

@@ -4,7 +4,7 @@
 //   D*u                      -> spmv_kernel            (coalesced value/index streams, sub-warp team per row)
 //   (a*Dxx + a*Dyy - ...)*u  -> spmv_multi_kernel      (all operators share ONE colind: one gather of u
 //                                                       serves every matrix, no scalar*sparse temporaries)
-//   E' * v                   -> spmv_t_kernel          (deterministic gather over a lazily built CSC view)
+//   E' * v                   -> spmv_t_csc_kernel      (deterministic, over a lazily built CSC copy: no atomics)
 // Bytes per row (algorithmic): 12 n + 16 for one matrix (8n values + 4n int32 indices + x + y).
 #include <cub/device/device_radix_sort.cuh>
 
@@ -77,24 +77,52 @@ __global__ void __launch_bounds__(256) spmv_multi_kernel(int64_t M, int n, const
     if (row < M && t == 0) y[row] = beta == 0.0 ? acc : acc + beta * y[row];
 }
 
-// y[c] = alpha * sum_{entries e in column c} vals[e] * v[e / n] + beta * y[c]   (one warp per column chunk)
-__global__ void spmv_t_kernel(int64_t N, int n, const int32_t* __restrict__ t_ptr, const int32_t* __restrict__ t_src,
-                              const double* __restrict__ vals, const double* __restrict__ v, double alpha, double beta,
-                              double* __restrict__ y) {
+// y[c] = alpha * sum_{entries e in column c} vals[e] * v[row(e)] + beta * y[c]: 8 lanes per column, entries of a column are
+// contiguous in the CSC view.  Owned operators read a CSC copy of the values (t_vals: three coalesced streams + the gather of
+// v, as the forward product); borrowed ones gather the caller's values through t_src.
+template <int KU>
+__global__ void spmv_t_csc_kernel(int64_t N, const int32_t* __restrict__ t_ptr, const int32_t* __restrict__ t_row,
+                                  const double* __restrict__ t_vals, const int32_t* __restrict__ t_src, const double* __restrict__ vals,
+                                  const double* __restrict__ v, double alpha, double beta, double* __restrict__ y) {
     const int lane = threadIdx.x & 7;
     const int64_t col = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 3;
-    double acc = 0.0;
+    double acc0 = 0.0, acc1 = 0.0;
     if (col < N) {
         const int b = t_ptr[col], e = t_ptr[col + 1];
-        for (int i = b + lane; i < e; i += 8) {
-            const int src = t_src[i];
-            acc += __ldg(vals + src) * __ldg(v + src / n);
+        for (int i0 = b + lane; i0 < e; i0 += 8 * KU) {  // KU entries per lane in flight, all loads before the first use
+            int r[KU];
+            double w[KU], x[KU];
+#pragma unroll
+            for (int k = 0; k < KU; ++k) {
+                const int i = i0 + 8 * k;
+                const bool in = i < e;
+                r[k] = in ? t_row[i] : -1;
+                w[k] = in ? (t_vals ? __ldcs(t_vals + i) : __ldg(vals + t_src[i])) : 0.0;
+            }
+#pragma unroll
+            for (int k = 0; k < KU; ++k) x[k] = r[k] >= 0 ? __ldg(v + r[k]) : 0.0;
+#pragma unroll
+            for (int k = 0; k < KU; k += 2) {
+                acc0 = fma(w[k], x[k], acc0);
+                acc1 = fma(w[k + 1], x[k + 1], acc1);
+            }
         }
     }
+    double acc = acc0 + acc1;
     acc += __shfl_xor_sync(0xffffffffu, acc, 4);
     acc += __shfl_xor_sync(0xffffffffu, acc, 2);
     acc += __shfl_xor_sync(0xffffffffu, acc, 1);
     if (col < N && lane == 0) y[col] = beta == 0.0 ? alpha * acc : alpha * acc + beta * y[col];
+}
+
+__global__ void transpose_rows_kernel(const int32_t* __restrict__ t_src, int64_t nnz, int n, int32_t* __restrict__ t_row) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < nnz) t_row[i] = t_src[i] / n;
+}
+
+__global__ void transpose_vals_kernel(const int32_t* __restrict__ t_src, const double* __restrict__ vals, int64_t nnz, double* __restrict__ t_vals) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < nnz) t_vals[i] = vals[t_src[i]];
 }
 
 __global__ void iota_kernel2(int* p, int64_t n) {
@@ -191,7 +219,7 @@ int rbffd_build_transpose(rbffd_operator* op) {
     cudaStream_t st = ctx->stream;
     const int64_t nnz = op->M * op->n;
     if (nnz > 0x7fffffff) RBFFD_FAIL(ctx, RBFFD_ERR_UNSUPPORTED, "transpose view needs nnz < 2^31 per shard");
-    DevBuf<int> ident, keys_sorted, src, ptr;
+    DevBuf<int> ident, keys_sorted, src, ptr, rowid;
     CUDA_TRY(ctx, ident.alloc(nnz, st));
     CUDA_TRY(ctx, keys_sorted.alloc(nnz, st));
     CUDA_TRY(ctx, src.alloc(nnz, st));
@@ -205,10 +233,13 @@ int rbffd_build_transpose(rbffd_operator* op) {
     CUDA_TRY(ctx, tmp.alloc(tmp_bytes, st));
     CUDA_TRY(ctx, cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, op->colind, keys_sorted.p, ident.p, src.p, (int)nnz, 0, bits, st));
     seg_start_kernel2<<<ceil_div_i64(nnz + 1, 256), 256, 0, st>>>(keys_sorted.p, nnz, (int)op->N, ptr.p);
+    CUDA_TRY(ctx, rowid.alloc(nnz, st));
+    transpose_rows_kernel<<<ceil_div_i64(std::max<int64_t>(nnz, 1), 256), 256, 0, st>>>(src.p, nnz, op->n, rowid.p);
     CUDA_TRY(ctx, cudaGetLastError());
     CUDA_TRY(ctx, cudaStreamSynchronize(st));
     op->t_ptr = ptr.release();
     op->t_src = src.release();
+    op->t_row = rowid.release();
     return RBFFD_OK;
 }
 
@@ -218,7 +249,22 @@ int rbffd_spmv_t_impl(rbffd_operator* op, int which, double alpha, const double*
     RBFFD_TRY(rbffd_build_transpose(op));
     if (op->N == 0) return RBFFD_OK;
     const double* vals = op->vals + (size_t)op->M * op->n * which;
-    spmv_t_kernel<<<ceil_div_i64(op->N, 256 / 8), 256, 0, ctx->stream>>>(op->N, op->n, op->t_ptr, op->t_src, vals, v, alpha, beta, y);
+    const int64_t nnz = op->M * (int64_t)op->n;
+    const double* tv = nullptr;
+    if (!op->borrowed && nnz > 0) {                      // values in column order, built once per matrix
+        if (op->t_vals.empty()) op->t_vals.assign(op->nmat, nullptr);
+        if (!op->t_vals[which]) {
+            double* p = nullptr;
+            CUDA_TRY(ctx, cudaMalloc((void**)&p, sizeof(double) * (size_t)nnz));
+            transpose_vals_kernel<<<ceil_div_i64(nnz, 256), 256, 0, ctx->stream>>>(op->t_src, vals, nnz, p);
+            KLAUNCH(ctx);
+            op->t_vals[which] = p;
+        }
+        tv = op->t_vals[which];
+    }
+    // columns hold about n entries: two per lane cover n <= 16 ... 40 in one or two trips, four per lane the larger stencils
+    if (op->n <= 40) spmv_t_csc_kernel<2><<<ceil_div_i64(op->N, 256 / 8), 256, 0, ctx->stream>>>(op->N, op->t_ptr, op->t_row, tv, op->t_src, vals, v, alpha, beta, y);
+    else spmv_t_csc_kernel<4><<<ceil_div_i64(op->N, 256 / 8), 256, 0, ctx->stream>>>(op->N, op->t_ptr, op->t_row, tv, op->t_src, vals, v, alpha, beta, y);
     KLAUNCH(ctx);
     CUDA_TRY(ctx, cudaGetLastError());
     return RBFFD_OK;
