@@ -334,9 +334,10 @@ int rbffd_generate_operator_host(rbffd_context* ctx, const rbffd_options* opts, 
         const unsigned hc = std::thread::hardware_concurrency();
         const unsigned lw = lw_env ? (unsigned)std::max(1, atoi(lw_env)) : 1u;
         const int T = wt_env ? std::max(1, atoi(wt_env)) : (int)std::min(8u, hc / (2 * lw));
-        // several ranks on one host: PCIe writes of all GPUs plus the widening traffic contend for host memory bandwidth
-        // (measured at N = 2: 11.1 ms per call with host widening), so the default there is the device-side widening
-        bool host_widen = hw_env ? atoi(hw_env) != 0 : (lw == 1 && T >= 4);
+        // Several ranks on one host share its ingest bandwidth (measured at N = 2: 16.3 ms per call when every rank ships the
+        // int64 pattern, 11.1 ms with the int32 pattern widened by 6 host threads per rank), so the smaller transfer stays the
+        // default as long as every rank gets at least 4 widening threads.
+        bool host_widen = hw_env ? atoi(hw_env) != 0 : T >= 4;
         constexpr int NSL = 8;
         struct Wideners {                          // joined on every exit path (the threads only wait for queued copies)
             std::vector<std::thread> th;
