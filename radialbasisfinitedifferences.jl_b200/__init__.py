@@ -6,5 +6,5 @@ from ._lib import AdvDiffParams, Options, RbffdError, build, exported_symbols, l
 from .api import (BoundaryConditions, Context, Operator, REFERENCE_OPS, calculateneighbors, default_context, generate_operator,  # noqa: F401
                   generate_operator_collocated, generate_raw, groups_from_index_sets, hyperviscosity_operator,
                   hyperviscosity_operator_collocated, make_options)
-from . import mesh, nodes  # noqa: F401
+from . import lsq, mesh, nodes  # noqa: F401
 from .sharding import PeerHalo, SlabShard, boundary_row_ranges, exchange_halo  # noqa: F401

@@ -50,6 +50,45 @@ def poisson_error(tominec, gen):
 
 
 
+def poisson_error_device(tominec, ctx):
+    """test/poisson_test.jl:19-132 with everything after the node sets on the device: operators generated into HBM, the
+    collocation matrix assembled from their row blocks (:76-79 with the scalings of :110-118), `u = D \\ f` (:121) by CGLS
+    over the library's SpMV / transposed SpMV, the evaluation `E*u` (:124) by SpMV."""
+    import torch
+    import rbffd_b200 as rb
+    from scipy.spatial import cKDTree
+    X = tominec["X"].copy()
+    Y = tominec["Y"].copy()
+    N, M = len(X), len(Y)
+    iin, idi, ine = tominec["Y_idx_in"] - 1, tominec["Y_idx_dirichlet"] - 1, tominec["Y_idx_neumann"] - 1
+    xn, yn = tominec["x_normals"][:, 2], tominec["y_normals"][:, 2]
+    nearest = cKDTree(Y).query(X, 1)[1]
+    for i in range(N):
+        Y[nearest[i]] = X[i]
+    dev = torch.device("cuda", ctx.device)
+    Xd, Yd = torch.from_numpy(X).to(dev), torch.from_numpy(Y).to(dev)
+    op = ctx.operator_generate(rb.make_options(2, 3, 20, 3, rb.REFERENCE_OPS), Xd.data_ptr(), N, Yd.data_ptr(), M)   # E Dx Dy Dxx Dyy Dxy
+    u_exact = lambda x, y: np.sin(2 * np.pi * x * y)
+    f2 = lambda x, y: -4.0 * x**2 * np.pi**2 * np.sin(2 * np.pi * x * y) - 4.0 * y**2 * np.pi**2 * np.sin(2 * np.pi * x * y)
+    f1 = lambda n1, n2, x, y: n2 * x * np.pi * np.cos(2 * np.pi * x * y) * 2.0 + n1 * y * np.pi * np.cos(2 * np.pi * x * y) * 2.0
+    h = np.mean(cKDTree(X).query(X, 2)[0][:, 1])
+    s0, s1, s2 = 1 / h / np.sqrt(len(idi)), 1 / np.sqrt(len(ine)), 1 / np.sqrt(len(iin))
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    D, keep = rb.lsq.mixed_row_operator(ctx, op, [(t(iin), [(3, float(s2)), (4, float(s2))]),
+                                                  (t(ine), [(1, t(xn * s1)), (2, t(yn * s1))]),
+                                                  (t(idi), [(0, float(s0))])], M)
+    f = np.zeros(M)
+    f[iin] = f2(Y[iin, 0], Y[iin, 1]) * s2
+    f[ine] = f1(xn, yn, Y[ine, 0], Y[ine, 1]) * s1
+    f[idi] = u_exact(Y[idi, 0], Y[idi, 1]) * s0
+    u, iters, rel = rb.lsq.cgls(D, 0, t(f), tol=1e-11)
+    uY = torch.empty(M, dtype=torch.float64, device=dev)
+    op.spmv_device(0, u.data_ptr(), uY.data_ptr())
+    ctx.synchronize()
+    ue = u_exact(Y[:, 0], Y[:, 1])
+    return float(np.linalg.norm(uY.cpu().numpy() - ue) / np.linalg.norm(ue)), iters, rel
+
+
 def mesh_import_error(cgns_path, X, gen, ctx=None):
     """test/mesh_import_test.jl:19-158 with `gen` standing in for generate_operator: Y comes from processmesh on the CGNS
     mesh (ghost nodes dropped, :52), Neumann normals from the mesh (:38-40), p = 3, polydeg = 5, n = 42."""

@@ -243,6 +243,19 @@ def test_two_set_oversampled_poisson(ctx, oracle, tominec):
     assert abs(err - 0.0026579) < 2e-6
 
 
+def test_poisson_reference_test_on_device(tominec):
+    """test/poisson_test.jl end to end on the device: operators in HBM, row-block collocation matrix, the least-squares solve
+    `u = D \\ f` (:121, sparse QR in the reference) by preconditioned CGLS over SpMV / transposed SpMV, `E*u` by SpMV.  Same
+    known answer as the host replay: rel. l2 error 0.0026579 < 0.0027 (:132)."""
+    import torch
+    from poisson_helper import poisson_error_device
+    c = rb.Context(0, stream=torch.cuda.current_stream().cuda_stream)
+    err, iters, rel = poisson_error_device(tominec, c)
+    assert rel <= 1e-11 and iters < 50000
+    assert err < float(tominec["poisson_threshold"])
+    assert abs(err - 0.0026579) < 2e-6
+
+
 def test_mesh_import_reference_test(ctx, tominec):
     """test/mesh_import_test.jl:158 (err < 0.001) through the GPU path: CGNS mesh -> processmesh (exact GPU 1-NN for the
     ghost offset and the normal orientation) -> generate_operator on the device -> the reference's least-squares solve."""
