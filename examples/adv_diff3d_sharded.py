@@ -41,7 +41,7 @@ def exact(X, t, alpha, a, x0, s0):
     return (s0 * s0 / s2) ** 1.5 * torch.exp(-d2 / (2.0 * s2))
 
 
-def run(g, steps, alpha=2e-3, a=(0.3, 0.2, 0.1), bw=None, cfl=0.08, combine=True):
+def run(g, steps, alpha=2e-3, a=(0.3, 0.2, 0.1), bw=None, cfl=0.08, combine=True, graph=False):
     import torch.distributed as dist
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -128,24 +128,45 @@ def run(g, steps, alpha=2e-3, a=(0.3, 0.2, 0.1), bw=None, cfl=0.08, combine=True
     dt = cfl * h * h / alpha
     u = exact(own, 0.0, alpha, a, x0, s0)
 
+    t_dev = torch.zeros((), dtype=torch.float64, device=dev)     # the time lives on the device: the step is replayable
+
     def stage(v, t):                                 # Dirichlet layer: exact solution at the stage time
-        v[bidx] = exact(Xb, t, alpha, a, x0, s0)
+        v.index_copy_(0, bidx, exact(Xb, t, alpha, a, x0, s0))
         return v
 
+    def rk3_step():                                  # SSP-RK3 (Shu-Osher)
+        v1 = stage(u + dt * rhs(u), t_dev + dt)
+        v2 = stage(0.75 * u + 0.25 * (v1 + dt * rhs(v1)), t_dev + 0.5 * dt)
+        u.copy_(stage(u / 3.0 + (2.0 / 3.0) * (v2 + dt * rhs(v2)), t_dev + dt))
+        t_dev.add_(dt)
+
+    replay, todo = rk3_step, steps
+    if graph and world == 1 and steps > 1:
+        # one GPU: the step is a fixed sequence of ~30 launches with static buffers -> captured ONCE into a CUDA graph (the
+        # context launches on the capture stream) and replayed.  With N > 1 the halo kernels carry an epoch argument that
+        # changes every exchange, so the step is not replayable as is.
+        rk3_step()
+        todo -= 1
+        torch.cuda.synchronize()
+        cg = torch.cuda.CUDAGraph()
+        main_stream = torch.cuda.current_stream().cuda_stream
+        with torch.cuda.graph(cg):
+            ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+            rk3_step()
+        ctx.set_stream(main_stream)
+        replay = cg.replay
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    t = 0.0
-    for _ in range(steps):
-        v1 = stage(u + dt * rhs(u), t + dt)
-        v2 = stage(0.75 * u + 0.25 * (v1 + dt * rhs(v1)), t + 0.5 * dt)
-        u = stage(u / 3.0 + (2.0 / 3.0) * (v2 + dt * rhs(v2)), t + dt)
-        t += dt
+    for _ in range(todo):
+        replay()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     t_run = time.perf_counter() - t0
+    t = steps * dt
+    steps_timed = max(todo, 1)
     ue = exact(own, t, alpha, a, x0, s0)
     acc = torch.stack([((u - ue) ** 2).sum(), (ue ** 2).sum(), u.sum(), (u * (own[:, 0] + 2 * own[:, 1] + 3 * own[:, 2])).sum()])
     tt = torch.tensor([t_gen, t_run], dtype=torch.float64, device=dev)
@@ -156,7 +177,8 @@ def run(g, steps, alpha=2e-3, a=(0.3, 0.2, 0.1), bw=None, cfl=0.08, combine=True
     out = {"example": "adv_diff3d_sharded", "n_gpus": world, "global_nodes": G ** 3, "nodes_per_gpu": M, "n": n, "p": P, "polydeg": DEG,
            "steps": steps, "dt": dt, "t_end": t, "rel_l2_error_vs_exact": err, "checksum": [float(acc[2]), float(acc[3])],
            "generation_s": float(tt[0]), "stencils_per_s": G ** 3 / float(tt[0]),
-           "ms_per_step": float(tt[1]) / steps * 1e3, "rhs_evaluations_per_s": 3 * steps / float(tt[1]),
+           "ms_per_step": float(tt[1]) / steps_timed * 1e3, "rhs_evaluations_per_s": 3 * steps_timed / float(tt[1]),
+           "cuda_graph": bool(graph and world == 1 and steps > 1),
            "operators_per_stage": 1 if combine else 4,
            "halo": "NVLink peer-memory stores (CUDA IPC)" if halo is not None else "none"}
     if halo is not None:
@@ -170,8 +192,9 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--no-combine", action="store_true", help="apply the four operators in every stage (fused multi-operator SpMV) "
                     "instead of pre-combining them into one matrix")
+    ap.add_argument("--graph", action="store_true", help="one GPU: capture the SSP-RK3 step into a CUDA graph and replay it")
     args = ap.parse_args()
-    out, _ = run(args.g, args.steps, combine=not args.no_combine)
+    out, _ = run(args.g, args.steps, combine=not args.no_combine, graph=args.graph)
     if int(os.environ.get("RANK", "0")) == 0:
         print(json.dumps(out))
     import torch.distributed as dist

@@ -588,7 +588,7 @@ def test_operator_combine(ctx, oracle):
         op.combine_device([0, 5], [1.0, 1.0], vc.data_ptr())
 
 
-def _run_example_3d(nproc, g, steps):
+def _run_example_3d(nproc, g, steps, extra=()):
     import json
     import os
     import subprocess
@@ -597,7 +597,7 @@ def _run_example_3d(nproc, g, steps):
     script = os.path.join(os.path.dirname(here), "examples", "adv_diff3d_sharded.py")
     cmd = [sys.executable, script] if nproc == 1 else [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(nproc),
                                                         "--master-addr", "127.0.0.1", "--master-port", "29583", script]
-    r = subprocess.run(cmd + ["--g", str(g), "--steps", str(steps)], capture_output=True, text=True, timeout=600)
+    r = subprocess.run(cmd + ["--g", str(g), "--steps", str(steps), *extra], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     return json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
 
@@ -609,6 +609,11 @@ def test_sharded_3d_time_stepping_example_one_gpu():
     out = _run_example_3d(1, 30, 12)
     assert out["global_nodes"] == 27000 and out["n"] == 60
     assert out["rel_l2_error_vs_exact"] < 2e-2, out
+    # the same run with the SSP-RK3 step replayed from a CUDA graph, and with the four operators applied separately
+    rep = _run_example_3d(1, 30, 12, ("--graph",))
+    assert rep["cuda_graph"] and rep["checksum"] == out["checksum"] and rep["rel_l2_error_vs_exact"] == out["rel_l2_error_vs_exact"]
+    sep = _run_example_3d(1, 30, 12, ("--no-combine",))
+    assert abs(sep["rel_l2_error_vs_exact"] - out["rel_l2_error_vs_exact"]) <= 1e-9 * out["rel_l2_error_vs_exact"]
 
 
 def test_sharded_3d_time_stepping_example_two_gpus():
