@@ -281,10 +281,11 @@ int rbffd_generate_operator_host(rbffd_context* ctx, const rbffd_options* opts, 
         CUDA_TRY(ctx, dG.alloc(N, st));
         CUDA_TRY(ctx, cudaMemcpyAsync(dG.p, xgroup, sizeof(int32_t) * N, cudaMemcpyHostToDevice, st));
     }
-    // Collocated rows with pinned output buffers: the column indices are known as soon as the neighbour search is done
-    // (they ARE the stencils), so their D2H starts right away on a second stream and runs under the weight solve; the
-    // rows are solved in chunks and every finished chunk of values follows on the same copy stream while the next chunk
-    // is being solved (the 480 MB D2H of config 2 costs more than the kernels).  Anything else takes the one-shot path.
+    // Collocated rows with pinned output buffers run as a pipeline: the column indices are known as soon as
+    // the neighbour search is done (they ARE the stencils), so they leave right away on a second stream under the weight
+    // solve; the rows are solved in a few shrinking chunks queued back to back, each followed on the copy stream by its
+    // values; status words are collected per chunk on the device and read once at the end.  Anything else takes the
+    // one-shot path below.
     cudaPointerAttributes pa_c, pa_v;
     const bool pinned = cudaPointerGetAttributes(&pa_c, colind_out) == cudaSuccess && pa_c.type == cudaMemoryTypeHost &&
                         cudaPointerGetAttributes(&pa_v, vals_out) == cudaSuccess && pa_v.type == cudaMemoryTypeHost;
