@@ -256,6 +256,19 @@ def test_poisson_reference_test_on_device(tominec):
     assert abs(err - 0.0026579) < 2e-6
 
 
+def test_mesh_import_reference_test_on_device(tominec):
+    """test/mesh_import_test.jl on the device (n = 42, polydeg = 5: the oversampled rows go through the multi-warp null-space
+    kernel, the least-squares solve through CGLS): err < 0.001 (:158), the host replay gives 4.70e-4."""
+    import os
+    import torch
+    from poisson_helper import mesh_import_error_device
+    c = rb.Context(0, stream=torch.cuda.current_stream().cuda_stream)
+    path = os.path.join(os.path.dirname(__file__), "golden", "tominec_Y.cgns")
+    err, iters, rel = mesh_import_error_device(path, tominec["X"], c)
+    assert rel <= 1e-11 and iters < 100000
+    assert err < 0.001 and abs(err - 4.70e-4) < 2e-6
+
+
 def test_mesh_import_reference_test(ctx, tominec):
     """test/mesh_import_test.jl:158 (err < 0.001) through the GPU path: CGNS mesh -> processmesh (exact GPU 1-NN for the
     ghost offset and the normal orientation) -> generate_operator on the device -> the reference's least-squares solve."""
