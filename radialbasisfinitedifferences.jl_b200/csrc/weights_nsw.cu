@@ -20,6 +20,7 @@
 // generate_operator.jl:55-65,89-182, hyperviscosity_operator.jl:97-161).
 #include <utility>
 
+#include <cstdlib>
 #include "common.cuh"
 #include "tables.cuh"
 #include "phs.cuh"
@@ -596,7 +597,9 @@ int launch_nsw2(rbffd_context* ctx, WNArgs& a) {
     auto kern = weights_nsw_kernel<D, Q, FOLD>;
     CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int per_sm = std::max<int>(1, std::min<int>(4, (int)((228 * 1024) / (smem + 1024))));
-    const int grid = (int)std::min<int64_t>(a.NS, (int64_t)ctx->sm_count * per_sm * 4);
+    // CTAs per resident slot (see weights_ns.cu): 4 -> 44.8 ms, 32 -> 43.9, 256 -> 41.3, one stencil per CTA -> 43.1 (config 4 shape)
+    static const int waves = [] { const char* e = getenv("RBFFD_NSW_WAVES"); const int w = e ? atoi(e) : 0; return w > 0 ? w : 256; }();
+    const int grid = (int)std::min<int64_t>(a.NS, (int64_t)ctx->sm_count * per_sm * waves);
 #ifdef NSW_TIMING
     unsigned long long zero[16] = {};
     cudaMemcpyToSymbolAsync(nsw_prof, zero, sizeof(zero), 0, cudaMemcpyHostToDevice, ctx->stream);
