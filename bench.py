@@ -105,11 +105,21 @@ class ClockSampler:
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def host_cores():
+    """hardware threads this process may run on (the affinity mask, not OMP_NUM_THREADS)"""
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
 def cpu_sample(sample_g, steps=1, threads=None):
     """Times the CPU oracle (reference arithmetic: kd-tree kNN, inv(A)*RHS per stencil, CSR SpMV) on a g^2 sample."""
     import numpy as np
     import rbffd_b200 as rb
     from oracle import oracle as orc
+    # all host cores, whatever the launcher exported: torch.distributed.run sets OMP_NUM_THREADS=1 for its workers
+    orc.set_num_threads(threads or host_cores())
     X = rb.nodes.jittered_lattice(CFG["dim"], sample_g, 0)
     N = len(X)
     best = None

@@ -74,6 +74,8 @@ int rbffd_create(int device, rbffd_context** ctx);
 int rbffd_destroy(rbffd_context* ctx);
 const char* rbffd_last_error(const rbffd_context* ctx);    /* valid until the next call on ctx; ctx may be NULL */
 int rbffd_set_stream(rbffd_context* ctx, void* cuda_stream); /* cudaStream_t owned by the caller (e.g. torch)   */
+int rbffd_get_stream(rbffd_context* ctx, void** cuda_stream);/* the stream the context launches on right now     */
+int rbffd_reset_stream(rbffd_context* ctx);                  /* back to the context's own (non-blocking) stream   */
 int rbffd_synchronize(rbffd_context* ctx);
 int rbffd_version(void);
 /* milliseconds (CUDA events) of the phases of the last generate call: [0] binning [1] knn [2] nearest

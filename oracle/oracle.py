@@ -50,6 +50,12 @@ def num_threads() -> int:
     return lib().orc_num_threads()
 
 
+def set_num_threads(nthreads: int) -> int:
+    """OpenMP threads of the oracle's parallel loops (overrides OMP_NUM_THREADS); returns the value now in effect."""
+    lib().orc_set_num_threads(int(nthreads))
+    return num_threads()
+
+
 def num_monomials(d: int, deg: int) -> int:
     return lib().orc_num_monomials(d, deg)
 

@@ -55,6 +55,16 @@ int orc_num_threads(void) {
 #endif
 }
 
+/* bench.py's reference arm: launchers such as torch.distributed.run export OMP_NUM_THREADS=1, which would silently
+ * turn the "all host cores" baseline into a single-thread run */
+void orc_set_num_threads(int nthreads) {
+#ifdef _OPENMP
+    if (nthreads > 0) omp_set_num_threads(nthreads);
+#else
+    (void)nthreads;
+#endif
+}
+
 /* ------------------------------------------------------------------------------------------------
  * kNN
  * ---------------------------------------------------------------------------------------------- */

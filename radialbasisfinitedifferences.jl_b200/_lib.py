@@ -62,6 +62,8 @@ _SIGNATURES = {
     "rbffd_destroy": ([_vp], C.c_int),
     "rbffd_last_error": ([_vp], C.c_char_p),
     "rbffd_set_stream": ([_vp, _vp], C.c_int),
+    "rbffd_get_stream": ([_vp, C.POINTER(_vp)], C.c_int),
+    "rbffd_reset_stream": ([_vp], C.c_int),
     "rbffd_synchronize": ([_vp], C.c_int),
     "rbffd_timings": ([_vp, C.POINTER(_dbl), C.c_int], C.c_int),
     "rbffd_knn_device": ([_vp, _vp, _i64, _i32, _vp, _i64, _i32, _vp, _vp, _vp, _vp], C.c_int),

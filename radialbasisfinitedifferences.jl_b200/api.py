@@ -103,6 +103,17 @@ class Context:
     def set_stream(self, stream: int):
         self._check(self._L.rbffd_set_stream(self._h, C.c_void_p(int(stream))))
 
+    @property
+    def stream(self) -> int:
+        """the cudaStream_t (as an int) the context launches on"""
+        s = C.c_void_p()
+        self._check(self._L.rbffd_get_stream(self._h, C.byref(s)))
+        return s.value or 0
+
+    def reset_stream(self):
+        """back to the context's own non-blocking stream"""
+        self._check(self._L.rbffd_reset_stream(self._h))
+
     def synchronize(self):
         self._check(self._L.rbffd_synchronize(self._h))
 
@@ -313,8 +324,10 @@ def _to_csc(colind, vals, shape_mode, N):
     return [sp.csr_matrix((v.ravel(), colind.ravel(), indptr), shape=(M, ncols)).tocsc() for v in vals]
 
 
-def generate_raw(X, Y, p, n, polydeg, ops=REFERENCE_OPS, groups=None, ctx=None, sort_columns=False, kernel=0, variant=0):
-    """colind [M, n] int64 (stencil order unless sort_columns), vals [nops, M, n]: the fixed-row CSR the kernels write."""
+def generate_raw(X, Y, p, n, polydeg, ops=REFERENCE_OPS, groups=None, ctx=None, sort_columns=False, kernel=0, variant=0,
+                 index_base=0):
+    """colind [M, n] int64 (stencil order unless sort_columns; index_base 0, or 1 as the Julia shim asks for),
+    vals [nops, M, n]: the fixed-row CSR the kernels write."""
     ctx = ctx or default_context()
     X = _coords(X, "X")
     Y = X if Y is None else _coords(Y, "Y")
@@ -322,7 +335,7 @@ def generate_raw(X, Y, p, n, polydeg, ops=REFERENCE_OPS, groups=None, ctx=None, 
         raise ValueError("DimensionMismatch: X and Y have different dimensions")
     N, dim = X.shape
     M = Y.shape[0]
-    opts = make_options(dim, p, n, polydeg, ops, 0, sort_columns, kernel, variant)
+    opts = make_options(dim, p, n, polydeg, ops, index_base, sort_columns, kernel, variant)
     colind = np.empty((M, n), np.int64)
     vals = np.empty((opts.nops, M, n), np.float64)
     g = None if groups is None else np.ascontiguousarray(groups, np.int32)

@@ -98,7 +98,7 @@ int rbffd_create(int device, rbffd_context** out) {
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
     for (int i = 0; i < 4 && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&ctx->chunk_ev[i], cudaEventDisableTiming);
     if (e == cudaSuccess) {
-        ctx->own_stream = true;
+        ctx->owned_stream = ctx->stream;
         for (int i = 0; i < 8 && e == cudaSuccess; ++i) e = cudaEventCreate(&ctx->ev[i]);
     }
     if (e == cudaSuccess) e = cudaHostAlloc((void**)&ctx->hflags, 16 * sizeof(int), cudaHostAllocMapped);
@@ -131,7 +131,7 @@ int rbffd_destroy(rbffd_context* ctx) {
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->hflags) cudaFreeHost(ctx->hflags);
     if (ctx->stage_i32) cudaFreeHost(ctx->stage_i32);
-    if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->owned_stream) cudaStreamDestroy(ctx->owned_stream);
     delete ctx;
     return RBFFD_OK;
 }
@@ -141,9 +141,19 @@ const char* rbffd_last_error(const rbffd_context* ctx) { return ctx ? ctx->err.c
 int rbffd_set_stream(rbffd_context* ctx, void* cuda_stream) {
     if (!ctx) return RBFFD_ERR_INVALID;
     cudaSetDevice(ctx->device);
-    if (ctx->own_stream && ctx->stream) { cudaStreamSynchronize(ctx->stream); cudaStreamDestroy(ctx->stream); }
-    ctx->stream = (cudaStream_t)cuda_stream;
-    ctx->own_stream = false;
+    ctx->stream = (cudaStream_t)cuda_stream;      // borrowed; the context's own stream is kept for rbffd_reset_stream
+    return RBFFD_OK;
+}
+
+int rbffd_get_stream(rbffd_context* ctx, void** cuda_stream) {
+    if (!ctx || !cuda_stream) return RBFFD_ERR_INVALID;
+    *cuda_stream = (void*)ctx->stream;
+    return RBFFD_OK;
+}
+
+int rbffd_reset_stream(rbffd_context* ctx) {
+    if (!ctx) return RBFFD_ERR_INVALID;
+    ctx->stream = ctx->owned_stream;
     return RBFFD_OK;
 }
 
@@ -324,6 +334,9 @@ int rbffd_generate_operator_host(rbffd_context* ctx, const rbffd_options* opts, 
         CUDA_TRY(ctx, c32.alloc((size_t)ch * n, st));
         CUDA_TRY(ctx, vb.alloc((size_t)M * n * nops, st));
         CUDA_TRY(ctx, dflags.alloc(8 * nchunks, st));
+        // Declared after every temporary the copy stream reads, so it runs BEFORE their destructors on every exit path
+        // (error returns included): the stream-ordered frees on `st` must not overtake D2H copies still in flight.
+        struct DrainCopies { cudaStream_t s; ~DrainCopies() { cudaStreamSynchronize(s); } } drain_copies{ctx->copy_stream};
         init_deferred_kernel<<<1, 8 * nchunks, 0, st>>>(dflags.p);
         KLAUNCH(ctx);
         // The pattern crosses PCIe as int32 (half the bytes of the caller's int64) into a pinned staging buffer, slice by

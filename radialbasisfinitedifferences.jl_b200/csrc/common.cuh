@@ -12,7 +12,7 @@
 struct rbffd_context {
     int device = 0;
     cudaStream_t stream = nullptr;
-    bool own_stream = false;
+    cudaStream_t owned_stream = nullptr;  // created by rbffd_create; `stream` points at it until rbffd_set_stream borrows another
     cudaStream_t copy_stream = nullptr;   // D2H of finished row chunks overlaps the weight kernel of the next chunk
     cudaEvent_t chunk_ev[4] = {nullptr, nullptr, nullptr, nullptr};
     std::string err;

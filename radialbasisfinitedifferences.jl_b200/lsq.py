@@ -37,6 +37,21 @@ def cgls(op, which, f, tol=1e-12, maxit=100000, check=200, precondition=True):
     import torch
     M, N, n = op.M, op.N, op.n
     dev = f.device
+    # the torch arithmetic below and the library's SpMVs must run on ONE stream: a Context created without stream= owns
+    # a non-blocking stream of its own, on which the products would race with the vector updates
+    ctx_stream = op.ctx.stream
+    op.ctx.set_stream(torch.cuda.current_stream(dev).cuda_stream)
+    try:
+        return _cgls(op, which, f, tol, maxit, check, precondition)
+    finally:
+        op.ctx.synchronize()
+        op.ctx.set_stream(ctx_stream)
+
+
+def _cgls(op, which, f, tol, maxit, check, precondition):
+    import torch
+    M, N, n = op.M, op.N, op.n
+    dev = f.device
     if precondition:                                    # column norms of D: D.^2' * 1 through the transposed product
         ci_ptr, v_ptr = op.pointers(which)
         class _Raw:

@@ -24,6 +24,15 @@ class SlabShard:
     g: int
     halo_rows: int
 
+    def __post_init__(self):
+        # A halo of `halo_rows` lattice rows is filled by ONE hop from the adjacent rank, so every rank must own at least
+        # that many rows; thinner slabs would make a neighbour ship rows out of its own (stale) halo.
+        if self.world > 1 and self.halo_rows > 0:
+            thinnest = min((self.g * (r + 1)) // self.world - (self.g * r) // self.world for r in range(self.world))
+            if thinnest < self.halo_rows:
+                raise ValueError(f"SlabShard: the thinnest slab owns {thinnest} lattice rows < halo_rows = {self.halo_rows}; "
+                                 "use fewer ranks, a larger lattice or a narrower halo (single-hop halo exchange)")
+
     @property
     def row_size(self) -> int:          # nodes per slowest-axis row (a line in 2-D, a plane in 3-D)
         return self.g ** (self.dim - 1)
@@ -129,12 +138,24 @@ def exchange_halo(u_local, shard: SlabShard, group=None, async_op=False):
 
 
 def boundary_row_ranges(shard: SlabShard):
-    """Owned rows split into (low boundary, interior, high boundary) half-open ranges: only rows within halo_rows
-    lattice rows of a slab face can reference halo columns (that is what halo_is_sufficient verified)."""
+    """Owned rows split into (low boundary, interior, high boundary) half-open ranges.  The split is geometric (rows within
+    halo_rows lattice rows of a slab face); that the interior rows really reference no halo column is NOT implied by
+    halo_is_sufficient -- check it with interior_rows_are_halo_free(colind, shard) before overlapping the interior rows
+    with a halo exchange."""
     s = shard
-    lo = min(s.n_owned, s.n_lo)                      # n_lo == halo_rows * row_size when a lower neighbour exists
+    lo = min(s.n_owned, s.n_lo)                      # n_lo == lo_rows * row_size (0 at the domain edge)
     hi = min(s.n_owned - lo, s.n_hi)
     return (0, lo), (lo, s.n_owned - hi), (s.n_owned - hi, s.n_owned)
+
+
+def interior_rows_are_halo_free(colind, shard: SlabShard) -> bool:
+    """True when no row of the interior range of boundary_row_ranges references a halo column, i.e. when those rows may be
+    applied while neighbours are still storing into the halo.  colind: [n_owned, n] local column ids (torch or NumPy)."""
+    (i0, i1) = boundary_row_ranges(shard)[1]
+    if i1 <= i0:
+        return True
+    ci = colind[i0:i1]
+    return bool(int(ci.min()) >= shard.n_lo and int(ci.max()) < shard.n_lo + shard.n_owned)
 
 
 class PeerHalo:
@@ -202,7 +223,12 @@ class PeerHalo:
         import ctypes as C
         self.ctx._check(self.ctx._L.rbffd_halo_ack_device(self.ctx._h, C.byref(self._h), self.epoch))
 
-    def close(self):
+    def close(self, group=None):
+        # collective: a neighbour's push / ack kernel may still be storing into this buffer
+        import torch.distributed as dist
+        self.ctx.synchronize()
+        if dist.is_initialized():
+            dist.barrier(group=group)
         for p in self._peers:
             self.ctx._L.rbffd_ipc_close(self.ctx._h, p)
         self._peers = []

@@ -104,6 +104,11 @@ CASES = [
     (3, 14, 7, 3, 60, ["Lap", "Dx", "Dy", "Dz"]),                       # config 4 shape
     (3, 12, 7, 3, 60, ["E", "Dx", "Dy", "Dz", "Dxx", "Dyy", "Dzz", "Dxy", "Dxz", "Dyz"]),
     (2, 30, 3, 3, 20, ["E", "Dx", "Dy", "Dxx", "Dyy", "Dxy"]),          # poisson_test.jl parameters
+    # hyperviscosity at the order the survey probed against sympy (p = 7, K = 6: hyperviscosity_operator.jl:26 with K < p)
+    (2, 36, 7, 5, 42, [("Dk", 0, 6), ("Dk", 1, 6), "Dxx"]),             # q = 21: multi-warp null-space kernel, zero polynomial RHS
+    (2, 30, 7, 6, 60, [("Dk", 0, 6), ("Dk", 1, 6), "Lap"]),             # q = 28: degree-6 monomials give the polynomial RHS 6!
+    (3, 12, 7, 3, 60, [("Dk", 2, 4), ("Dk", 0, 4), "Lap"]),             # 3-D d^4/dz^4 and d^4/dx^4 (extension of :26 to d = 3)
+    (3, 12, 7, 4, 70, [("Dk", 2, 4), ("Dk", 1, 6)]),                    # 3-D, q = 35, degree-4 monomials hit by d^4/dz^4
 ]
 
 
@@ -226,6 +231,36 @@ def test_sorted_pattern_bit_exact(ctx, oracle):
     scol, svals = oracle.sort_rows(rcol, list(rvals))
     assert np.array_equal(colind, scol)
     _check_weights(vals, np.stack(svals), cond)
+
+
+def test_sorted_one_based_pattern_is_the_reference_sparse_matrix(ctx, oracle, tominec):
+    """What the Julia shim hands to SparseMatrixCSC: sort_columns = 1 and index_base = 1 (julia/RBFFDB200.jl).  The fixed-row
+    CSR (rowptr = 1 + k n, 1-based sorted column ids, values) read as the CSC of the TRANSPOSE must be, entry for entry, the
+    matrix `sparse(vec(idx_rows), vec(idx_columns), vec(W))` builds (generate_operator.jl:171-182): same size (max I, max J),
+    same stored entries (zeros kept), strictly increasing row ids inside every column of the transpose."""
+    import scipy.sparse as sp
+    X, Y = tominec["X"], tominec["Y"]
+    p, n, deg = 3, 30, 4
+    ops = ["E", "Dx", "Dyy"]
+    c1, v1 = rb.generate_raw(X, Y, p, n, deg, ops, ctx=ctx, sort_columns=True, index_base=1)
+    c0, v0 = rb.generate_raw(X, Y, p, n, deg, ops, ctx=ctx)                      # stencil order, 0-based
+    M = len(Y)
+    assert c1.min() >= 1 and c1.max() <= len(X)
+    assert np.all(np.diff(c1, axis=1) > 0)                                         # sorted, no duplicates (kNN ids are distinct)
+    rowptr1 = 1 + n * np.arange(M + 1)                                             # what the shim passes as colptr
+    rcol, rvals = oracle.generate_operator(X, Y, p, n, deg, ops=ops)
+    assert np.array_equal(c0, rcol)
+    for o in range(len(ops)):
+        # Julia: SparseMatrixCSC(N, M, colptr, rowval, nzval) is D' ; here: the same three arrays, 1-based -> 0-based
+        Dt = sp.csc_matrix((v1[o].ravel(), c1.ravel() - 1, rowptr1 - 1), shape=(int(c1.max()), M))
+        assert Dt.has_sorted_indices
+        # the reference's COO -> CSC assembly from the unsorted stencil-order triplets of the GPU path
+        rows = np.repeat(np.arange(M), n)
+        ref = sp.coo_matrix((v0[o].ravel(), (rows, c0.ravel())), shape=(M, int(c0.max()) + 1)).tocsc()
+        D = Dt.T.tocsc()
+        assert D.shape == ref.shape and D.nnz == ref.nnz == M * n
+        assert np.array_equal(D.indptr, ref.indptr) and np.array_equal(D.indices, ref.indices)
+        assert np.array_equal(D.data, ref.data)                                    # sorting moves values, never changes them
 
 
 def test_two_set_oversampled_poisson(ctx, oracle, tominec):

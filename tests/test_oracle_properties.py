@@ -225,3 +225,76 @@ def test_legacy_collocated_method(oracle):
     rel = lambda a_, b_: np.abs(a_ - b_).max() / np.abs(b_).max()
     assert rel(vals[3][interior], v2[3][interior]) < 0.2          # Dxx: same operator up to the anisotropic-scaling effect
     assert rel(vals[1][interior], v2[1][interior]) > 1e-3         # Dx: the sign quirk is really there
+
+
+def _twoset_numpy(X, Y, idx, center, rows, p, polydeg):
+    """Line-by-line numpy replay of the two-set generate_operator(X, Y, p, n, polydeg) (src/generate_operator.jl:29-190)
+    for the Y rows `rows`, with LAPACK doing what LinearAlgebra does there: scalestencil (src/scalestencil.jl:10-20),
+    A = [Phi P; P' 0] (src/interpolationmatrix.jl:5), numpy.linalg.inv = getrf + getri (:8), inv(A) * RHS (:158), chain-rule
+    factors (:161-166).  Returns [6, len(rows), n] in the order E, Dx, Dy, Dxx, Dyy, Dxy, and cond_1(A) per row."""
+    eps = np.finfo(float).eps
+    ex = [(a, g - a) for g in range(polydeg + 1) for a in range(g, -1, -1)]
+    n = idx.shape[1]
+    out = np.zeros((6, len(rows), n))
+    cond = np.zeros(len(rows))
+    for kk, k in enumerate(rows):
+        c = center[k]
+        st = idx[c]
+        Xs = X[st] - X[st[0]]
+        sx, sy = 1.0 / np.abs(Xs[:, 0]).max(), 1.0 / np.abs(Xs[:, 1]).max()
+        S = Xs * np.array([sx, sy])
+        d = S[:, None, :] - S[None, :, :]
+        Phi = np.sqrt((d ** 2).sum(-1)) ** p
+        P = np.stack([S[:, 0] ** a * S[:, 1] ** b for a, b in ex], 1)
+        q = P.shape[1]
+        A = np.block([[Phi, P], [P.T, np.zeros((q, q))]])
+        Ainv = np.linalg.inv(A)
+        cond[kk] = np.abs(A).sum(0).max() * np.abs(Ainv).sum(0).max()
+        ys = (Y[k] - X[st[0]]) * np.array([sx, sy])
+        dx, dy = ys[0] - S[:, 0], ys[1] - S[:, 1]
+        dx[dx == 0] = eps
+        dy[dy == 0] = eps
+        r = np.hypot(dx, dy)
+        b = r ** p
+        bx, by = p * dx * r ** (p - 2), p * dy * r ** (p - 2)
+        bxx = p * r ** (p - 2) + p * (p - 2) * dx ** 2 * r ** (p - 4)
+        byy = p * r ** (p - 2) + p * (p - 2) * dy ** 2 * r ** (p - 4)
+        bxy = p * (p - 2) * dx * dy * r ** (p - 4)
+
+        def mono(a, b_, da, db):          # d^(da,db) of x^a y^b_ at the scaled evaluation point (polylinearoperator.jl:36-44)
+            if a < da or b_ < db:
+                return 0.0
+            ca = float(np.prod([a - t for t in range(da)])) if da else 1.0
+            cb = float(np.prod([b_ - t for t in range(db)])) if db else 1.0
+            return ca * cb * ys[0] ** (a - da) * ys[1] ** (b_ - db)
+        cols = []
+        for (da, db), rb_ in (((0, 0), b), ((1, 0), bx), ((0, 1), by), ((2, 0), bxx), ((0, 2), byy), ((1, 1), bxy)):
+            cols.append(np.concatenate([rb_, [mono(a, b_, da, db) for a, b_ in ex]]))
+        W = Ainv @ np.stack(cols, 1)
+        f = [1.0, sx, sy, sx * sx, sy * sy, sx * sy]
+        for o in range(6):
+            out[o, kk] = f[o] * W[:n, o]
+    return out, cond
+
+
+def test_twoset_weights_against_lapack_inverse(oracle, tominec):
+    """Pins the oracle's weight-level arithmetic (mode 0: LU + explicit inverse + inv(A)*RHS) to a real LAPACK getrf/getri on
+    the reference's own two-set fixture (test/data/x_nodes_fitted.csv, y_nodes_fitted.csv; Y != X, eta != 0 rows): the
+    oracle and the numpy replay of generate_operator.jl:29-190 must agree to 10 eps cond_1(A) per row, for all six
+    operators, at the parameters of test/poisson_test.jl:56-60."""
+    X, Y = tominec["X"], tominec["Y"]
+    p, n, deg = 3, 2 * 15, 4            # poisson_test.jl: rbfdeg = 3, polydeg = 4, n = 2 * binomial(polydeg + 2, 2)
+    colind, vals, cond_x = oracle.generate_operator(X, Y, p, n, deg, want_cond=True)
+    idx, _ = oracle.knn(X, X, n)
+    center = oracle.knn(X, Y, 1)[0][:, 0]
+    assert np.array_equal(colind, idx[center])
+    rows = np.random.default_rng(5).choice(len(Y), 400, replace=False)
+    ref, cond = _twoset_numpy(X, Y, idx, center, rows, p, deg)
+    assert np.allclose(cond, cond_x[center[rows]], rtol=1e-6)        # same matrices on both sides
+    eps = np.finfo(float).eps
+    worst = 0.0
+    for o in range(6):
+        err = np.abs(vals[o][rows] - ref[o]).max(1)
+        tol = 10 * eps * cond * np.abs(ref[o]).max(1)
+        worst = max(worst, (err / tol).max())
+    assert worst <= 1.0, f"oracle vs LAPACK inverse: {worst:.2f} x (10 eps cond)"
