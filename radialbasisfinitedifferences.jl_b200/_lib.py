@@ -10,7 +10,8 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "librbffd.so")
+# RBFFD_LIB selects a development build of the SAME library (kernel experiments, e.g. built with EXTRA=-DNSW_TIMING)
+LIB_PATH = os.environ.get("RBFFD_LIB") or os.path.join(_HERE, "librbffd.so")
 MAX_OPS = 12
 
 OK, ERR_INVALID, ERR_K_TOO_LARGE, ERR_SINGULAR, ERR_CUDA, ERR_UNSUPPORTED = range(6)

@@ -9,72 +9,18 @@
 #include <cub/device/device_radix_sort.cuh>
 
 #include "common.cuh"
+#include "spmv_rows.cuh"
 
 namespace {
 
-// TPR lanes cooperate on one row; a warp covers 32/TPR consecutive rows = one contiguous chunk of HBM.
-// Every lane first issues ALL of its value/index loads (streaming, evict-first), then the gathers of x
-// (read-only path, kept in L1/L2), then the FMAs: ITERS*VEC independent loads in flight per lane.
-// VEC = 2 uses 16-byte value loads and 8-byte index loads (needs an even row length: rows stay 16-byte aligned).
 template <int TPR, int NMAT, int VEC, int ITERS>
 __global__ void __launch_bounds__(256) spmv_multi_kernel(int64_t M, int n, const int32_t* __restrict__ colind,
                                                          const double* __restrict__ v0, const double* __restrict__ v1,
                                                          const double* __restrict__ v2, const double* __restrict__ v3,
                                                          double c0, double c1, double c2, double c3,
                                                          const double* __restrict__ x, double beta, double* __restrict__ y) {
-    const int lane = threadIdx.x & 31;
-    const int t = lane % TPR;
     const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
-    const int64_t row = warp * (32 / TPR) + lane / TPR;
-    double acc = 0.0;
-    if (row < M) {
-        const int64_t base = row * n;
-        int col[ITERS][VEC];
-        double w[ITERS][VEC];
-#pragma unroll
-        for (int it = 0; it < ITERS; ++it) {
-            const int j = (t + it * TPR) * VEC;
-            if (VEC == 2) {
-                if (j < n) {
-                    const int2 ci = __ldcs(reinterpret_cast<const int2*>(colind + base + j));
-                    double2 a0 = __ldcs(reinterpret_cast<const double2*>(v0 + base + j));
-                    a0.x *= c0; a0.y *= c0;
-                    if (NMAT > 1) { const double2 b = __ldcs(reinterpret_cast<const double2*>(v1 + base + j)); a0.x += c1 * b.x; a0.y += c1 * b.y; }
-                    if (NMAT > 2) { const double2 b = __ldcs(reinterpret_cast<const double2*>(v2 + base + j)); a0.x += c2 * b.x; a0.y += c2 * b.y; }
-                    if (NMAT > 3) { const double2 b = __ldcs(reinterpret_cast<const double2*>(v3 + base + j)); a0.x += c3 * b.x; a0.y += c3 * b.y; }
-                    col[it][0] = ci.x; col[it][VEC - 1] = ci.y;
-                    w[it][0] = a0.x; w[it][VEC - 1] = a0.y;
-                } else {
-                    col[it][0] = col[it][VEC - 1] = -1;
-                    w[it][0] = w[it][VEC - 1] = 0.0;
-                }
-            } else {
-                if (j < n) {
-                    col[it][0] = __ldcs(colind + base + j);
-                    double a0 = c0 * __ldcs(v0 + base + j);
-                    if (NMAT > 1) a0 += c1 * __ldcs(v1 + base + j);
-                    if (NMAT > 2) a0 += c2 * __ldcs(v2 + base + j);
-                    if (NMAT > 3) a0 += c3 * __ldcs(v3 + base + j);
-                    w[it][0] = a0;
-                } else {
-                    col[it][0] = -1;
-                    w[it][0] = 0.0;
-                }
-            }
-        }
-        double xv[ITERS][VEC];
-#pragma unroll
-        for (int it = 0; it < ITERS; ++it)
-#pragma unroll
-            for (int e = 0; e < VEC; ++e) xv[it][e] = col[it][e] >= 0 ? __ldg(x + col[it][e]) : 0.0;
-#pragma unroll
-        for (int it = 0; it < ITERS; ++it)
-#pragma unroll
-            for (int e = 0; e < VEC; ++e) acc = fma(w[it][e], xv[it][e], acc);
-    }
-#pragma unroll
-    for (int o = TPR / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if (row < M && t == 0) y[row] = beta == 0.0 ? acc : acc + beta * y[row];
+    spmv_rows<TPR, NMAT, VEC, ITERS, false>(warp, 0, M, n, colind, v0, v1, v2, v3, c0, c1, c2, c3, x, nullptr, 0, beta, y);
 }
 
 // y[c] = alpha * sum_{entries e in column c} vals[e] * v[row(e)] + beta * y[c]: 8 lanes per column, entries of a column are

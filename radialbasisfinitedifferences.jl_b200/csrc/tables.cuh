@@ -111,6 +111,24 @@ __device__ __forceinline__ double rhs_rbf_entry(const OpTables& T, int o, const 
     return v;
 }
 
+// term-list evaluation without a division: rinv = 1/r is already known to the caller (r^e for e < 0 is rinv^|e|)
+template <int D>
+__device__ __forceinline__ double eval_rbf_terms_rinv(const OpTables& T, int b, int e, const double* del, double r, double r2, double rinv) {
+    const double ri2 = rinv * rinv;
+    double s = 0.0;
+    for (int t = b; t < e; ++t) {
+        double v = T.coef[t];
+#pragma unroll
+        for (int a = 0; a < D; ++a) v *= ipow_u(del[a], T.te[t][a]);
+        const int ex = T.te[t][3], ae = ex < 0 ? -ex : ex;
+        const double base1 = ex < 0 ? rinv : r, base2 = ex < 0 ? ri2 : r2;
+        double pw = (ae & 1) ? base1 : 1.0;
+        for (int u = 0; u < (ae >> 1); ++u) pw *= base2;
+        s = fma(v, pw, s);
+    }
+    return s;
+}
+
 // closed forms for operators of total order <= 2 and the Laplacian (the reference's standard tuple); higher orders
 // (hyperviscosity) go through the term tables.  rp2 = r^(p-2), rp4 = r^(p-4), rp = r^p for this offset.
 template <int D>

@@ -414,6 +414,9 @@ int rbffd_weights_ns(rbffd_context* ctx, const OpTables& T, const double* X, int
 // multi-warp null-space path (weights_nsw.cu): n <= 64, n - q <= 48; UNSUPPORTED also when a stencil fails its checks
 int rbffd_weights_nsw(rbffd_context* ctx, const OpTables& T, const double* X, int64_t N, const double* Y, int64_t M,
                       const int32_t* stencils, const int32_t* center, int32_t* colind_out, double* vals_out);
+// two-stage null-space path (weights_ns2.cu): same scope as weights_nsw.cu, P reduction in its own one-warp-per-stencil kernel
+int rbffd_weights_ns2(rbffd_context* ctx, const OpTables& T, const double* X, int64_t N, const double* Y, int64_t M,
+                      const int32_t* stencils, const int32_t* center, int32_t* colind_out, double* vals_out);
 // multi-warp register/DMMA path for 48 < m <= 96 (weights_mw.cu)
 int rbffd_weights_mw(rbffd_context* ctx, const OpTables& T, const double* X, int64_t N, const double* Y, int64_t M,
                      const int32_t* stencils, int32_t* colind_out, double* vals_out, int* fail_flag);
@@ -468,6 +471,7 @@ int rbffd_weights_impl(rbffd_context* ctx, const rbffd_options* opts, const doub
     const bool rowwise = !identity && opts->kernel != 1 && opts->kernel != 2 && opts->variant == 0;
     if (rowwise) {
         rc = rbffd_weights_ns(ctx, T, X, M, Y, M, stencils, center, colind_out, vals_out, flags.p);
+        if (rc == RBFFD_ERR_UNSUPPORTED && T.n > 32) rc = rbffd_weights_ns2(ctx, T, X, M, Y, M, stencils, center, colind_out, vals_out);
         if (rc == RBFFD_ERR_UNSUPPORTED && T.n > 32) rc = rbffd_weights_nsw(ctx, T, X, M, Y, M, stencils, center, colind_out, vals_out);
         if (rc != RBFFD_OK && rc != RBFFD_ERR_UNSUPPORTED) return rc;
         if (opts->kernel == 3 && rc != RBFFD_OK) RBFFD_FAIL(ctx, RBFFD_ERR_UNSUPPORTED, "null-space kernel not applicable (n=%d, q=%d) or a stencil failed its definiteness check", T.n, T.q);
@@ -475,6 +479,7 @@ int rbffd_weights_impl(rbffd_context* ctx, const rbffd_options* opts, const doub
     if (identity && opts->kernel != 1 && opts->variant == 0) {
         if (opts->kernel != 2) {
             rc = rbffd_weights_ns(ctx, T, X, N, Y, M, stencils, nullptr, colind_out, vals_out, flags.p);
+            if (rc == RBFFD_ERR_UNSUPPORTED && T.n > 32) rc = rbffd_weights_ns2(ctx, T, X, N, Y, M, stencils, nullptr, colind_out, vals_out);
             if (rc == RBFFD_ERR_UNSUPPORTED && T.n > 32) rc = rbffd_weights_nsw(ctx, T, X, N, Y, M, stencils, nullptr, colind_out, vals_out);
             if (rc != RBFFD_OK && rc != RBFFD_ERR_UNSUPPORTED) return rc;
             if (opts->kernel == 3 && rc != RBFFD_OK) RBFFD_FAIL(ctx, RBFFD_ERR_UNSUPPORTED, "null-space kernel not applicable (n=%d, q=%d) or a stencil failed its definiteness check", T.n, T.q);

@@ -476,7 +476,10 @@ int launch_ns(rbffd_context* ctx, NArgs& a) {
     constexpr int QP = 4 * ((Q + 3) / 4);
     a.bs = (a.T.nops + 1) & ~1;
     a.smem_per_warp = ((32 * NS_US + 32 * QP + 32 * a.bs + 32 * (D == 2 ? 2 : 4)) * 8 + 32 * 4 + 15) & ~15;
-    const size_t smem = (size_t)a.smem_per_warp * 4;
+    const size_t smem_used = (size_t)a.smem_per_warp * 4;
+    // development knob: RBFFD_NS_PAD_SMEM = extra dynamic shared memory per CTA (occupancy sweeps)
+    static const int pad_smem = [] { const char* e = getenv("RBFFD_NS_PAD_SMEM"); return e ? atoi(e) : 0; }();
+    const size_t smem = smem_used + (size_t)std::max(0, pad_smem);
     if ((int64_t)smem > ctx->max_smem_optin) return RBFFD_ERR_UNSUPPORTED;
     // 4 CTAs (16 warps) per SM when the shared-memory tile allows it, else 3
     const bool four = (smem + 1024) * 4 <= 228 * 1024;
@@ -489,7 +492,8 @@ int launch_ns(rbffd_context* ctx, NArgs& a) {
     // CTAs per resident slot: many short CTAs balance better than a few long grid-stride loops and keep the concurrently
     // processed stencils in a compact window of the node array (sweep 1..100000: 8 -> 5.38 ms, 128 -> 5.05 ms, more is flat)
     static const int waves = [] { const char* e = getenv("RBFFD_NS_WAVES"); const int w = e ? atoi(e) : 0; return w > 0 ? w : 128; }();
-    const int grid = (int)std::min<int64_t>(blocks_needed, (int64_t)ctx->sm_count * (four ? 4 : 3) * waves);
+    const int resident = std::max<int>(1, std::min<int>(four ? 4 : 3, (int)((228 * 1024) / (smem + 1024))));
+    const int grid = (int)std::min<int64_t>(blocks_needed, (int64_t)ctx->sm_count * resident * waves);
     kern<<<grid, 128, smem, ctx->stream>>>(a);
     KLAUNCH(ctx);
     CUDA_TRY(ctx, cudaGetLastError());

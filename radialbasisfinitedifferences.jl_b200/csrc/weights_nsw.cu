@@ -40,6 +40,7 @@ struct WNArgs {
     double gzval[8];
     int32_t lapcol[3];         // column of x_a^2 (-1: degree < 2)
     int32_t bs;                // row stride of the RBF right-hand-side tile
+    int32_t rot;               // 1: warp roles rotate with the CTA index
     OpTables T;
 };
 
@@ -187,8 +188,13 @@ __global__ void __launch_bounds__(128, 4) weights_nsw_kernel(WNArgs a) {
     using C = WnCfg<D, Q, FOLD>;
     constexpr int LD = WN_LD, KS = C::KS, QP = C::QP, NJ = C::NJ, US = C::US, DP = C::DP, CS = C::CS, NBP = WN_NBP;
     extern __shared__ __align__(16) unsigned char wsm[];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // Warp ROLES rotate with the CTA index: a CTA's warp w sits on scheduler partition w of the SM, so without the rotation
+    // the same role of all resident CTAs (the P reduction, the owner of the first panels) would share one partition.
+    const int tid = threadIdx.x, lane = tid & 31, warp = ((tid >> 5) + a.rot * (int)blockIdx.x) & 3;
     const int g = lane >> 2, t = lane & 3;
+#ifdef NSW_TIMING
+    const int rtid = warp * 32 + lane;
+#endif
     const OpTables& T = a.T;
     const int n = T.n, nops = T.nops, nb = n - Q, BS = a.bs;
     double* G = reinterpret_cast<double*>(wsm);
@@ -238,8 +244,8 @@ __global__ void __launch_bounds__(128, 4) weights_nsw_kernel(WNArgs a) {
         }
         unsigned kmin = 0xffffffffu;
         int bad = 0;
-        NSW_T(0, tid == 0);
-        NSW_T(9, tid == 64);
+        NSW_T(0, rtid == 0);
+        NSW_T(9, rtid == 64);
         if (warp < 2) {
             // ---- A1. column reduction of [P; g']: thread L2 < n holds row L2 of P, thread n + o the row g_o' ----
             double prow[Q];
@@ -319,7 +325,7 @@ __global__ void __launch_bounds__(128, 4) weights_nsw_kernel(WNArgs a) {
 #pragma unroll
                 for (int c = 0; c < QP; c += 2) dst[c >> 1] = make_double2(c < Q ? prow[c] : 0.0, c + 1 < Q ? prow[c + 1] : 0.0);
             }
-            NSW_T(1, tid == 0);
+            NSW_T(1, rtid == 0);
         } else {
             // ---- A2. Phi in original stencil order by symmetric pairs (round k pairs node l with (l + k) mod n), and
             //          the RBF part of the right-hand sides (generate_operator.jl:123-154) ----
@@ -344,11 +350,11 @@ __global__ void __launch_bounds__(128, 4) weights_nsw_kernel(WNArgs a) {
             }
             bar_named(2, 64);
             phs_assemble<D, DP, LD>(Sc, G, sx, l, n, L2 < n, hp);
-            NSW_T(2, tid == 64);
+            NSW_T(2, rtid == 64);
         }
         __syncthreads();
-        NSW_T(3, tid == 0);
-        NSW_T(4, tid == 64);
+        NSW_T(3, rtid == 0);
+        NSW_T(4, rtid == 64);
         // ---- B. Y = Phi~[:, N] - Phi~[:, B] W : row tiles 2*warp, 2*warp+1; permutation applied while gathering ----
         {
             double cy[2][NJ][2];
@@ -392,7 +398,7 @@ __global__ void __launch_bounds__(128, 4) weights_nsw_kernel(WNArgs a) {
                     *reinterpret_cast<double2*>(Yb + (8 * (2 * warp + ii) + g) * US + 8 * J + 2 * t) = make_double2(cy[ii][J][0], cy[ii][J][1]);
         }
         __syncthreads();
-        NSW_T(5, tid == 0);
+        NSW_T(5, rtid == 0);
         // ---- C. [S | t] = Y[N, :] - W' Y[B, :] : this warp owns tile columns warp and warp + 4 ----
         double c[6][2][2];
         const bool has2 = warp + 4 < NJ;
@@ -440,7 +446,7 @@ __global__ void __launch_bounds__(128, 4) weights_nsw_kernel(WNArgs a) {
             }
         }
         __syncthreads();                                  // the Y tile is dead: its storage becomes the exchange buffers
-        NSW_T(6, tid == 0);
+        NSW_T(6, rtid == 0);
         // ---- D. blocked Gauss-Jordan WITHOUT pivoting on the definite S (static pivot rows 4kb .. 4kb+3), with one
         //         step of lookahead: in step kb the owner of panel kb+1 updates that tile column first and eliminates the
         //         next panel while the other warps are still applying update kb ----
@@ -510,7 +516,7 @@ __global__ void __launch_bounds__(128, 4) weights_nsw_kernel(WNArgs a) {
         }(std::make_integer_sequence<int, 12>{});
         if (bad < 0 || kmin < 64u) *a.redo = 1;
         __syncthreads();
-        NSW_T(7, tid == 0);                                  // every pivot reciprocal is published; Bt is dead (Ys aliases it)
+        NSW_T(7, rtid == 0);                                  // every pivot reciprocal is published; Bt is dead (Ys aliases it)
         // y = RHS_row / pivot_row  (right-hand-side column rcb + o lives in tile (rcb + o) / 8)
         if (tid < nops) pf[tid] = op_post_factor<D>(T, tid, s);
 #pragma unroll
@@ -577,7 +583,7 @@ __global__ void __launch_bounds__(128, 4) weights_nsw_kernel(WNArgs a) {
             }
         }
         __syncthreads();
-        NSW_T(8, tid == 0);
+        NSW_T(8, rtid == 0);
     }
 }
 
@@ -595,8 +601,14 @@ int launch_nsw2(rbffd_context* ctx, WNArgs& a) {
     const size_t smem = ((size_t)(C::G + C::WT + C::SC + C::CAND + 64 * a.bs + 8) * 8 + 4 * 4 + 64 * 4 + 16 + 15) & ~(size_t)15;
     if ((int64_t)smem > ctx->max_smem_optin) return RBFFD_ERR_UNSUPPORTED;
     auto kern = weights_nsw_kernel<D, Q, FOLD>;
-    CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int per_sm = std::max<int>(1, std::min<int>(4, (int)((228 * 1024) / (smem + 1024))));
+    // development knobs: RBFFD_NSW_PAD_SMEM = extra dynamic shared memory per CTA (occupancy sweeps), RBFFD_NSW_ROT = 0/1
+    static const int pad_smem = [] { const char* e = getenv("RBFFD_NSW_PAD_SMEM"); return e ? atoi(e) : 0; }();
+    static const int rot = [] { const char* e = getenv("RBFFD_NSW_ROT"); return e ? atoi(e) : 0; }();   // measured: 1 costs 12 % at config 4 (r02a)
+    a.rot = rot;
+    const size_t smem_launch = smem + (size_t)std::max(0, pad_smem);
+    if ((int64_t)smem_launch > ctx->max_smem_optin) return RBFFD_ERR_UNSUPPORTED;
+    CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_launch));
+    const int per_sm = std::max<int>(1, std::min<int>(4, (int)((228 * 1024) / (smem_launch + 1024))));
     // CTAs per resident slot (see weights_ns.cu): 4 -> 44.8 ms, 32 -> 43.9, 256 -> 41.3, one stencil per CTA -> 43.1 (config 4 shape)
     static const int waves = [] { const char* e = getenv("RBFFD_NSW_WAVES"); const int w = e ? atoi(e) : 0; return w > 0 ? w : 256; }();
     const int grid = (int)std::min<int64_t>(a.NS, (int64_t)ctx->sm_count * per_sm * waves);
@@ -604,7 +616,7 @@ int launch_nsw2(rbffd_context* ctx, WNArgs& a) {
     unsigned long long zero[16] = {};
     cudaMemcpyToSymbolAsync(nsw_prof, zero, sizeof(zero), 0, cudaMemcpyHostToDevice, ctx->stream);
 #endif
-    kern<<<grid, 128, smem, ctx->stream>>>(a);
+    kern<<<grid, 128, smem_launch, ctx->stream>>>(a);
     KLAUNCH(ctx);
     CUDA_TRY(ctx, cudaGetLastError());
 #ifdef NSW_TIMING
