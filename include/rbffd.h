@@ -213,10 +213,85 @@ int rbffd_halo_push_device(rbffd_context* ctx, const rbffd_halo* h, uint32_t epo
 int rbffd_halo_wait_device(rbffd_context* ctx, const rbffd_halo* h, uint32_t epoch);
 int rbffd_halo_ack_device(rbffd_context* ctx, const rbffd_halo* h, uint32_t epoch);
 
+/* ---- spatial-block sharding of arbitrary node sets (BASELINE.json north_star: "nodes are partitioned by spatial blocks
+ *      across the 8 GPUs of one box").  The reference has no distributed code (src/domains/domains.jl:7-8).
+ *      One process per GPU.  Generation needs no communication: every rank searches its own nodes among
+ *      [owned | candidate halo] coordinates.  Application needs ONE halo exchange per product, fused into the SpMV launch:
+ *      peers store their values straight into this rank's inbox over NVLink (CUDA IPC), boundary rows wait for the flags.
+ *      Local numbering of a shard: [interior owned rows | boundary owned rows | halo]; "boundary" = references a halo column.
+ *      All vectors handed to rbffd_shard_spmv* hold the n_owned owned values in that local order. ---- */
+#define RBFFD_ERR_HALO 6          /* candidate halo too thin: a stencil could reach past the nodes held locally */
+#define RBFFD_SHARD_MAX_PEERS 16
+typedef struct rbffd_shard rbffd_shard;
+/* Partition N nodes into nparts spatial blocks: a b0 x b1 [x b2] grid whose cut planes are coordinate quantiles (every block of
+ * one slab holds the same number of nodes +-1).  blocks = NULL or zeros: the factorisation with the smallest cut surface.
+ * part_out[i] in [0, nparts).  Host only (no device needed). */
+int rbffd_shard_plan_host(const double* X, int64_t N, int32_t dim, int32_t nparts, const int32_t* blocks, int32_t* part_out);
+/* Build the shard of `rank` from the full node set and the partition (host arrays): owned = part == rank; candidate halo =
+ * foreign nodes inside the owned bounding box inflated by a margin (grown until the exactness proof below holds). */
+int rbffd_shard_create_host(rbffd_context* ctx, const double* X, int64_t N, int32_t dim, const int32_t* part, int32_t nparts,
+                            int32_t rank, int32_t n, rbffd_shard** shard);
+/* Same from device-resident candidates: Xc [nc][dim], gid [nc] (ASCENDING global ids: ties of the neighbour search are then
+ * broken by global id, as on one GPU), owner [nc].  box_lo/hi[dim] delimit the region all of whose nodes are among the
+ * candidates (+-infinity where nothing lies beyond).  Exactness proof: every owned stencil's radius is smaller than the
+ * distance of its centre to the faces of that box; otherwise RBFFD_ERR_HALO. */
+int rbffd_shard_create_device(rbffd_context* ctx, int32_t dim, int32_t n, const double* Xc, const int64_t* gid, const int32_t* owner,
+                              int64_t nc, const double* box_lo, const double* box_hi, int32_t rank, int32_t nparts, rbffd_shard** shard);
+int rbffd_shard_destroy(rbffd_shard* shard);
+int rbffd_shard_info(const rbffd_shard* shard, int64_t* n_owned, int64_t* n_interior, int64_t* n_halo);
+/* local id -> global id, n_owned + n_halo entries */
+int rbffd_shard_global_ids_host(rbffd_shard* shard, int32_t index_base, int64_t* gid_out);
+/* device arrays of the shard: coordinates [n_owned + n_halo][dim] and stencils [n_owned][n] (local ids, entry 0 = the row's node):
+ * feed them to rbffd_weights_device(ctx, opts, X_local, n_owned + n_halo, X_local, n_owned, stencils, n_owned, NULL, ...). */
+int rbffd_shard_device_arrays(const rbffd_shard* shard, const double** X_local, const int32_t** stencils);
+/* halo nodes this rank needs from `peer` (count, then global ids in halo order); the caller ships the lists to the peers
+ * (torch.distributed / MPI all-to-all) and hands every rank the lists addressed to it: */
+int rbffd_shard_recv_count(const rbffd_shard* shard, int32_t peer, int64_t* count);
+int rbffd_shard_recv_ids_host(rbffd_shard* shard, int32_t peer, int32_t index_base, int64_t* ids_out);
+int rbffd_shard_set_send_ids_host(rbffd_shard* shard, int32_t peer, int32_t index_base, const int64_t* ids, int64_t count);
+/* after all send lists are set: allocates the IPC inbox [halo values | flags | reverse inbox]; handle64 = cudaIpcMemHandle_t.
+ * offsets[2 * nparts + 1]: for every peer p, offsets[2p] = where ITS values land in my inbox (doubles), offsets[2p + 1] = where
+ * its transposed-product contributions land in my buffer (doubles; -1: none); offsets[2 * nparts] = byte offset of my flag
+ * block.  The caller all-gathers handle + offsets (torch.distributed / MPI) and connects every peer it exchanges with: */
+int rbffd_shard_finalize(rbffd_shard* shard, unsigned char* handle64, int64_t* offsets);
+/* fwd_offset = the peer's offsets[2 * me], rev_offset = the peer's offsets[2 * me + 1], flags_offset = the peer's offsets[2 * nparts] */
+int rbffd_shard_connect(rbffd_shard* shard, int32_t peer, const unsigned char* handle64, int64_t fwd_offset, int64_t rev_offset,
+                        int64_t flags_offset);
+/* y[0:n_owned] = sum_i coef[i] * D[which[i]] * [x ; halo of x]   (nterms <= 4), `op` = operators over the shard's local pattern
+ * (rows n_owned, columns n_owned + n_halo).  ONE kernel launch: the first CTAs store x's boundary values into the peers'
+ * inboxes and publish the epoch, interior rows run meanwhile, the CTAs of the boundary rows wait for the peers' flags, the
+ * last of them acknowledges.  The epoch lives in device memory: the call can be captured into a CUDA graph.
+ * Every rank must make the same sequence of rbffd_shard_spmv* calls. */
+int rbffd_shard_spmv_device(rbffd_shard* shard, rbffd_operator* op, int32_t nterms, const int32_t* which, const double* coef,
+                            const double* x, double* y);
+/* y[0:n_owned] = alpha * D[which]' * v + beta * y : the transposed product E' * v of adv_diff_test.jl:151 on a sharded operator.
+ * Contributions to halo columns travel back to their owners (reverse exchange) and are added in rank order (deterministic). */
+int rbffd_shard_spmv_t_device(rbffd_shard* shard, rbffd_operator* op, int32_t which, double alpha, const double* v, double beta, double* y);
+/* transport-agnostic form of the two exchanges (single-process tests, NCCL / gloo / MPI transports): pack = the values of x
+ * this rank owes `peer` (count = what the peer asked for), unpack = fill the halo segment owned by `peer` from its packed values;
+ * rbffd_shard_spmv_local_device is the same product as rbffd_shard_spmv_device WITHOUT any exchange (inbox filled by unpack). */
+int rbffd_shard_pack_device(rbffd_shard* shard, int32_t peer, const double* x, double* sendbuf);
+int rbffd_shard_unpack_device(rbffd_shard* shard, int32_t peer, const double* recvbuf);
+int rbffd_shard_spmv_local_device(rbffd_shard* shard, rbffd_operator* op, int32_t nterms, const int32_t* which, const double* coef,
+                                  const double* x, double* y);
+/* transposed product in three steps: local part (y = alpha D' v restricted to owned columns + beta y; the halo-column sums stay
+ * inside the shard), tpack = the sums owed to `peer` (recv_count(peer) doubles, contiguous), tunpack_add = add `peer`'s sums
+ * to the nodes it had asked for (send order).  Call tunpack_add in ascending peer order to reproduce rbffd_shard_spmv_t_device. */
+int rbffd_shard_spmv_t_local_device(rbffd_shard* shard, rbffd_operator* op, int32_t which, double alpha, const double* v, double beta, double* y);
+int rbffd_shard_tpack_device(rbffd_shard* shard, int32_t peer, double* sendbuf);
+int rbffd_shard_tunpack_add_device(rbffd_shard* shard, int32_t peer, const double* recvbuf, double* y);
+/* number of values this rank sends to `peer` per product (= what the peer's recv list asked for) */
+int rbffd_shard_send_count(const rbffd_shard* shard, int32_t peer, int64_t* count);
+
 /* ---- synthetic node sets: jittered lattice in [0,1]^d, counter-based RNG, on device ------ */
 /* node (i,j[,l]) of a g^d lattice, linear ids [first, first+count): ((i,j,l)+0.5+0.5*(U-0.5))/g */
 int rbffd_jittered_lattice_device(rbffd_context* ctx, int32_t dim, int64_t g, uint64_t seed,
                                   int64_t first, int64_t count, double* X_out);
+/* the nodes of the lattice box [lo, hi) (lattice coordinates per axis), enumerated in ascending global linear id; also writes
+ * the ids and, when blocks != NULL, the owner of every node under the regular blocks[dim] block partition of the lattice
+ * (block index along axis a = (c_a * blocks[a]) / g, owner = (b0 * blocks[1] + b1) * blocks[2] + b2 with x slowest) */
+int rbffd_jittered_lattice_box_device(rbffd_context* ctx, int32_t dim, int64_t g, uint64_t seed, const int64_t* lo, const int64_t* hi,
+                                      const int32_t* blocks, double* X_out, int64_t* gid_out, int32_t* owner_out);
 
 #ifdef __cplusplus
 }

@@ -14,7 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("RBFFD_LIB") or os.path.join(_HERE, "librbffd.so")
 MAX_OPS = 12
 
-OK, ERR_INVALID, ERR_K_TOO_LARGE, ERR_SINGULAR, ERR_CUDA, ERR_UNSUPPORTED = range(6)
+OK, ERR_INVALID, ERR_K_TOO_LARGE, ERR_SINGULAR, ERR_CUDA, ERR_UNSUPPORTED, ERR_HALO = range(7)
 OP_DERIV, OP_LAPLACE = 0, 1
 
 
@@ -103,6 +103,28 @@ _SIGNATURES = {
     "rbffd_gather_device": ([_vp, _vp, _vp, _i64, _vp], C.c_int),
     "rbffd_scatter_add_device": ([_vp, _vp, _vp, _i64, _vp], C.c_int),
     "rbffd_jittered_lattice_device": ([_vp, _i32, _i64, C.c_uint64, _i64, _i64, _vp], C.c_int),
+    "rbffd_jittered_lattice_box_device": ([_vp, _i32, _i64, C.c_uint64, _vp, _vp, _vp, _vp, _vp, _vp], C.c_int),
+    "rbffd_shard_plan_host": ([_vp, _i64, _i32, _i32, _vp, _vp], C.c_int),
+    "rbffd_shard_create_host": ([_vp, _vp, _i64, _i32, _vp, _i32, _i32, _i32, C.POINTER(_vp)], C.c_int),
+    "rbffd_shard_create_device": ([_vp, _i32, _i32, _vp, _vp, _vp, _i64, _vp, _vp, _i32, _i32, C.POINTER(_vp)], C.c_int),
+    "rbffd_shard_destroy": ([_vp], C.c_int),
+    "rbffd_shard_info": ([_vp, C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i64)], C.c_int),
+    "rbffd_shard_global_ids_host": ([_vp, _i32, _vp], C.c_int),
+    "rbffd_shard_device_arrays": ([_vp, C.POINTER(_vp), C.POINTER(_vp)], C.c_int),
+    "rbffd_shard_recv_count": ([_vp, _i32, C.POINTER(_i64)], C.c_int),
+    "rbffd_shard_send_count": ([_vp, _i32, C.POINTER(_i64)], C.c_int),
+    "rbffd_shard_recv_ids_host": ([_vp, _i32, _i32, _vp], C.c_int),
+    "rbffd_shard_set_send_ids_host": ([_vp, _i32, _i32, _vp, _i64], C.c_int),
+    "rbffd_shard_finalize": ([_vp, _vp, _vp], C.c_int),
+    "rbffd_shard_connect": ([_vp, _i32, _vp, _i64, _i64, _i64], C.c_int),
+    "rbffd_shard_spmv_device": ([_vp, _vp, _i32, C.POINTER(_i32), C.POINTER(_dbl), _vp, _vp], C.c_int),
+    "rbffd_shard_spmv_local_device": ([_vp, _vp, _i32, C.POINTER(_i32), C.POINTER(_dbl), _vp, _vp], C.c_int),
+    "rbffd_shard_spmv_t_device": ([_vp, _vp, _i32, _dbl, _vp, _dbl, _vp], C.c_int),
+    "rbffd_shard_spmv_t_local_device": ([_vp, _vp, _i32, _dbl, _vp, _dbl, _vp], C.c_int),
+    "rbffd_shard_pack_device": ([_vp, _i32, _vp, _vp], C.c_int),
+    "rbffd_shard_unpack_device": ([_vp, _i32, _vp], C.c_int),
+    "rbffd_shard_tpack_device": ([_vp, _i32, _vp], C.c_int),
+    "rbffd_shard_tunpack_add_device": ([_vp, _i32, _vp, _vp], C.c_int),
 }
 
 
