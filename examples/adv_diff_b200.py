@@ -6,11 +6,13 @@ methods, and integrates `cons_sys` with SSPRK43.  With `--mesh file.cgns` the no
 rb.mesh.processmesh (BASELINE config 1: examples/rect_0_10.cgns, markers left/right/top/bottom, adv_diff_test.jl:24-29);
 without it the node set is a synthetic rectangle [0,5]x[0,1] (interior jittered lattice + boundary midpoints + ghost
 nodes offset along the outward normal, the layout src/processmesh.jl:174-186 produces).  Every operator is generated on
-the GPU in ONE call (one kNN, one factorisation per node, 7 right-hand sides) and stays in HBM; each RK stage is
-    du = rhs_advdiff(u)           (rbffd_rhs_advdiff_device: fused multi-operator SpMV + E' + hyperviscosity)
-    ghost update of u             (rbffd_bc_apply_device)
-on the device, the stage combinations are torch axpys.  SSP-RK3 with a fixed step stands in for the adaptive SSPRK43
-of OrdinaryDiffEq (third-party, not part of the reference package).
+the GPU in ONE call (one kNN, one factorisation per node, 7 right-hand sides) and stays in HBM; each RK stage is three
+library launches and no torch arithmetic:
+    du = cons_sys interior line   (rbffd_rhs_advdiff_device; rows are collocated, so E = I and all six operators are applied
+                                   in ONE pass over the shared pattern; --general keeps the E' product of the reference)
+    ghost update of the stage     (rbffd_bc_apply_device: all four boundaries in one launch, in the reference's order)
+    stage combination             (rbffd_stage_update_device: a*u + b*(v + dt*du), with the UPDATED ghosts as in the reference)
+SSP-RK3 with a fixed step stands in for the adaptive SSPRK43 of OrdinaryDiffEq (third-party, not part of the reference package).
 """
 import argparse
 import os
@@ -53,7 +55,7 @@ def mesh_nodes(path, ctx=None):
     return X, idx_in, idx_bc, idx_g, float(np.sqrt(d2.min(1)).mean())
 
 
-def run(gy=40, steps=50, verbose=True, mesh=None, graph=False):
+def run(gy=40, steps=50, verbose=True, mesh=None, graph=False, collocated=True, timing=None):
     import torch
     dev = torch.device("cuda:0")
     X, idx_in, idx_bc, idx_g, h = mesh_nodes(mesh) if mesh else rectangle_nodes(gy)
@@ -73,7 +75,8 @@ def run(gy=40, steps=50, verbose=True, mesh=None, graph=False):
     bcs = rb.BoundaryConditions(op, [{"bc": list(idx_bc[b]), "ghost": list(idx_g[b]), **({"matrix": m} if m is not None else {"value": 1.0})}
                                      for b, m in order])
     alpha, ux, uy, k = 1.0, 0.0, 0.0, 2                                  # adv_diff_test.jl:88-94
-    prm = rb.AdvDiffParams(iE=0, iDx=1, iDy=2, iDxx=3, iDyy=4, iDxk=5, iDyk=6, alpha=alpha, ux=ux, uy=uy, gamma=100.0 * h ** (2 * k))
+    prm = rb.AdvDiffParams(iE=0, iDx=1, iDy=2, iDxx=3, iDyy=4, iDxk=5, iDyk=6, alpha=alpha, ux=ux, uy=uy, gamma=100.0 * h ** (2 * k),
+                           flags=rb.ADVDIFF_COLLOCATED if collocated else 0)
     u = torch.from_numpy(np.where((X[:, 0] - 0.5) ** 2 + (X[:, 1] - 0.5) ** 2 <= 0.04, 10.0, 1.0)).to(dev)   # :65
     du, u1, u2 = torch.empty_like(u), torch.empty_like(u), torch.empty_like(u)
 
@@ -85,18 +88,20 @@ def run(gy=40, steps=50, verbose=True, mesh=None, graph=False):
     # (the reference leaves the step size to the adaptive SSPRK43 controller)
     dt = 0.0025 * h * h / alpha
 
-    def rk3_step():                                                      # SSP-RK3 (Shu-Osher)
+    P = lambda t: t.data_ptr()
+
+    def rk3_step():                                                      # SSP-RK3 (Shu-Osher); every line is one library launch
         cons_sys(du, u)
-        torch.add(u, du, alpha=dt, out=u1)
+        ctx.stage_update_device(N, 0.0, P(u), 1.0, P(u), dt, P(du), P(u1))              # u1 = u + dt du
         cons_sys(du, u1)
-        u2.copy_(0.75 * u + 0.25 * (u1 + dt * du))
+        ctx.stage_update_device(N, 0.75, P(u), 0.25, P(u1), dt, P(du), P(u2))           # u2 = 3/4 u + 1/4 (u1 + dt du)
         cons_sys(du, u2)
-        u.copy_(u / 3.0 + (2.0 / 3.0) * (u2 + dt * du))
+        ctx.stage_update_device(N, 1.0 / 3.0, P(u), 2.0 / 3.0, P(u2), dt, P(du), P(u))  # u = 1/3 u + 2/3 (u2 + dt du)
 
     replay = rk3_step
     if graph and steps > 1:
-        # The step is a fixed sequence of ~40 small launches over a few thousand nodes (config 1): launch-bound.  One eager
-        # step builds the lazily allocated scratch (transpose view, work vector), then the step is captured ONCE into a CUDA
+        # The step is a fixed sequence of 9 small launches over a few thousand nodes (config 1): launch-bound.  One eager
+        # step builds the lazily allocated scratch and answers 'is E the identity', then the step is captured ONCE into a CUDA
         # graph on torch's capture stream (the context launches on whatever stream it is given) and replayed.
         rk3_step()
         steps -= 1
@@ -115,6 +120,8 @@ def run(gy=40, steps=50, verbose=True, mesh=None, graph=False):
     torch.cuda.synchronize()
     t_step = (time.perf_counter() - t0) / max(steps, 1)
     uh = u.cpu().numpy()
+    if timing is not None:
+        timing.update({"ms_per_step": t_step * 1e3, "generation_ms": t_gen * 1e3, "nodes": N, "launches_per_step": 9 if collocated else 15})
     if verbose:
         print(f"N = {N} nodes, n = {n}, generation {t_gen * 1e3:.1f} ms (7 operators), {t_step * 1e3:.3f} ms per SSP-RK3 step "
               f"(3 RHS evaluations{', CUDA graph replay' if graph else ''}), u in [{uh.min():.4f}, {uh.max():.4f}]")
@@ -127,5 +134,6 @@ if __name__ == "__main__":
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--mesh", default=None, help="CGNS mesh (e.g. tests/golden/rect_0_10.cgns = BASELINE config 1)")
     ap.add_argument("--graph", action="store_true", help="capture the SSP-RK3 step once into a CUDA graph and replay it")
+    ap.add_argument("--general", action="store_true", help="keep the E' product of cons_sys (three products per evaluation) instead of using E = I")
     a = ap.parse_args()
-    run(a.gy, a.steps, mesh=a.mesh, graph=a.graph)
+    run(a.gy, a.steps, mesh=a.mesh, graph=a.graph, collocated=not a.general)

@@ -63,7 +63,9 @@ typedef struct {
                            1 = legacy collocated methods generate_operator(X, p, n, polydeg) (generate_operator.jl:354) and
                                hyperviscosity_operator(K, X, p, n, polydeg) (hyperviscosity_operator.jl:314): no scaling,
                                centre node moved to (eps, eps), RBF right-hand sides evaluated at X_j - x_c.  Y must be X. */
-    int32_t reserved[4];
+    int32_t index_width; /* 0 or 64: host index arrays are int64 (SparseMatrixCSC{Float64,Int64}); 32: rbffd_generate_operator_host
+                            writes int32 indices into colind_out (a SparseMatrixCSC{Float64,Int32}: half the PCIe bytes, no widening pass) */
+    int32_t reserved[3];
 } rbffd_options;
 
 typedef struct rbffd_context rbffd_context;     /* one per (device, stream); not thread-safe, thread-compatible */
@@ -109,6 +111,7 @@ int rbffd_calculateneighbors_host(rbffd_context* ctx, const double* X, int64_t N
  * hyperviscosity_operator(K, X, Y, p, n, polydeg[, index sets]) (hyperviscosity_operator.jl:26, :177):
  * one neighbour search and ONE factorisation per X node serve every operator in opts->ops.
  * Y == NULL means Y = X.  colind_out[M*n] and vals_out[nops*M*n] are caller-allocated host buffers. */
+/* colind_out: int64 [M*n], or int32 [M*n] passed through the same pointer when opts->index_width == 32 */
 int rbffd_generate_operator_host(rbffd_context* ctx, const rbffd_options* opts,
                                  const double* X, int64_t N, const double* Y, int64_t M,
                                  const int32_t* xgroup, int64_t* colind_out, double* vals_out);
@@ -164,10 +167,29 @@ int rbffd_spmv_t_host(rbffd_operator* op, int32_t which, double alpha, const dou
  * iDxk/iDyk < 0 drops the hyperviscosity term.  u, du: device, length N (= M). */
 typedef struct {
     int32_t iE, iDx, iDy, iDxx, iDyy, iDxk, iDyk;
-    int32_t reserved;
+    int32_t flags;      /* RBFFD_ADVDIFF_* */
     double alpha, ux, uy, gamma;
 } rbffd_advdiff_params;
+/* rows are collocated with the nodes (Y == X, as in adv_diff_test.jl): E is then the identity, and what the weight solve returns
+ * for it deviates from I by rounding noise only (eps * cond(A_i)).  When max|E - I| <= 1e-8 (checked once per operator, outside
+ * CUDA-graph capture) E' * w is taken as w and the whole line becomes ONE pass over the shared pattern with up to six value
+ * planes; the result differs from the three-product form by that noise (|E - I| relative), and is the more accurate of the two. */
+#define RBFFD_ADVDIFF_COLLOCATED 1
 int rbffd_rhs_advdiff_device(rbffd_operator* op, const rbffd_advdiff_params* prm, const double* u, double* du);
+/* out = a*u + b*(x + dt * cons_sys(x)): one Shu-Osher stage of an SSP-RK scheme (the reference hands cons_sys to
+ * OrdinaryDiffEq's SSPRK43, adv_diff_test.jl:196-199) with the right-hand side of rbffd_rhs_advdiff_device; ONE launch on the
+ * collocated path.  out must not alias x or u. */
+int rbffd_rhs_advdiff_stage_device(rbffd_operator* op, const rbffd_advdiff_params* prm, const double* x, double a, const double* u,
+                                   double b, double dt, double* out);
+/* out[i] = a*u[i] + b*(x[i] + dt*du[i]), i < N: the stage combination alone, for right-hand sides that mutate their argument
+ * between the product and the combination (cons_sys updates the ghost nodes of u AFTER du is formed, adv_diff_test.jl:151-176,
+ * and the integrator then combines the updated u with du).  Element-wise: out may alias u or x. */
+int rbffd_stage_update_device(rbffd_context* ctx, int64_t N, double a, const double* u, double b, const double* x, double dt,
+                              const double* du, double* out);
+/* out = a*u + b*(x + dt * sum_i coef[i] * D[which[i]] * x), nterms <= 6, rows = nodes (M == N): the same stage for any
+ * linear semidiscretisation over the shared pattern, ONE launch */
+int rbffd_spmv_stage_device(rbffd_operator* op, int32_t nterms, const int32_t* which, const double* coef, const double* x,
+                            double a, const double* u, double b, double dt, double* out);
 int rbffd_rhs_advdiff_host(rbffd_operator* op, const rbffd_advdiff_params* prm, const double* u, double* du);
 
 /* ---- ghost-node boundary updates of cons_sys (examples/adv_diff_test.jl:118-141 set-up, :162-176 per call) ---- */
@@ -257,7 +279,7 @@ int rbffd_shard_finalize(rbffd_shard* shard, unsigned char* handle64, int64_t* o
 /* fwd_offset = the peer's offsets[2 * me], rev_offset = the peer's offsets[2 * me + 1], flags_offset = the peer's offsets[2 * nparts] */
 int rbffd_shard_connect(rbffd_shard* shard, int32_t peer, const unsigned char* handle64, int64_t fwd_offset, int64_t rev_offset,
                         int64_t flags_offset);
-/* y[0:n_owned] = sum_i coef[i] * D[which[i]] * [x ; halo of x]   (nterms <= 4), `op` = operators over the shard's local pattern
+/* y[0:n_owned] = sum_i coef[i] * D[which[i]] * [x ; halo of x]   (nterms <= 6), `op` = operators over the shard's local pattern
  * (rows n_owned, columns n_owned + n_halo).  ONE kernel launch: the first CTAs store x's boundary values into the peers'
  * inboxes and publish the epoch, interior rows run meanwhile, the CTAs of the boundary rows wait for the peers' flags, the
  * last of them acknowledges.  The epoch lives in device memory: the call can be captured into a CUDA graph.
@@ -267,6 +289,10 @@ int rbffd_shard_spmv_device(rbffd_shard* shard, rbffd_operator* op, int32_t nter
 /* y[0:n_owned] = alpha * D[which]' * v + beta * y : the transposed product E' * v of adv_diff_test.jl:151 on a sharded operator.
  * Contributions to halo columns travel back to their owners (reverse exchange) and are added in rank order (deterministic). */
 int rbffd_shard_spmv_t_device(rbffd_shard* shard, rbffd_operator* op, int32_t which, double alpha, const double* v, double beta, double* y);
+/* out[0:n_owned] = a*u + b*(x + dt * sum_i coef[i] * D[which[i]] * [x ; halo of x]): one SSP-RK stage of the sharded
+ * semidiscretisation as ONE launch (halo exchange + product + stage update); out must not alias x or u */
+int rbffd_shard_spmv_stage_device(rbffd_shard* shard, rbffd_operator* op, int32_t nterms, const int32_t* which, const double* coef,
+                                  const double* x, double a, const double* u, double b, double dt, double* out);
 /* transport-agnostic form of the two exchanges (single-process tests, NCCL / gloo / MPI transports): pack = the values of x
  * this rank owes `peer` (count = what the peer asked for), unpack = fill the halo segment owned by `peer` from its packed values;
  * rbffd_shard_spmv_local_device is the same product as rbffd_shard_spmv_device WITHOUT any exchange (inbox filled by unpack). */

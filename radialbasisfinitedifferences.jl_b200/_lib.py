@@ -16,6 +16,7 @@ MAX_OPS = 12
 
 OK, ERR_INVALID, ERR_K_TOO_LARGE, ERR_SINGULAR, ERR_CUDA, ERR_UNSUPPORTED, ERR_HALO = range(7)
 OP_DERIV, OP_LAPLACE = 0, 1
+ADVDIFF_COLLOCATED = 1
 
 
 class RbffdError(RuntimeError):
@@ -27,7 +28,7 @@ class RbffdError(RuntimeError):
 class Options(C.Structure):
     _fields_ = [("dim", C.c_int32), ("p", C.c_int32), ("polydeg", C.c_int32), ("n", C.c_int32), ("nops", C.c_int32),
                 ("ops", (C.c_int32 * 4) * MAX_OPS), ("index_base", C.c_int32), ("sort_columns", C.c_int32),
-                ("kernel", C.c_int32), ("variant", C.c_int32), ("reserved", C.c_int32 * 4)]
+                ("kernel", C.c_int32), ("variant", C.c_int32), ("index_width", C.c_int32), ("reserved", C.c_int32 * 3)]
 
 
 class Halo(C.Structure):
@@ -38,7 +39,7 @@ class Halo(C.Structure):
 
 class AdvDiffParams(C.Structure):
     _fields_ = [("iE", C.c_int32), ("iDx", C.c_int32), ("iDy", C.c_int32), ("iDxx", C.c_int32), ("iDyy", C.c_int32),
-                ("iDxk", C.c_int32), ("iDyk", C.c_int32), ("reserved", C.c_int32),
+                ("iDxk", C.c_int32), ("iDyk", C.c_int32), ("flags", C.c_int32),
                 ("alpha", C.c_double), ("ux", C.c_double), ("uy", C.c_double), ("gamma", C.c_double)]
 
 
@@ -88,6 +89,10 @@ _SIGNATURES = {
     "rbffd_spmv_host": ([_vp, _i32, _dbl, _vp, _dbl, _vp], C.c_int),
     "rbffd_spmv_t_host": ([_vp, _i32, _dbl, _vp, _dbl, _vp], C.c_int),
     "rbffd_rhs_advdiff_device": ([_vp, C.POINTER(AdvDiffParams), _vp, _vp], C.c_int),
+    "rbffd_rhs_advdiff_stage_device": ([_vp, C.POINTER(AdvDiffParams), _vp, _dbl, _vp, _dbl, _dbl, _vp], C.c_int),
+    "rbffd_stage_update_device": ([_vp, _i64, _dbl, _vp, _dbl, _vp, _dbl, _vp, _vp], C.c_int),
+    "rbffd_spmv_stage_device": ([_vp, _i32, C.POINTER(_i32), C.POINTER(_dbl), _vp, _dbl, _vp, _dbl, _dbl, _vp], C.c_int),
+    "rbffd_shard_spmv_stage_device": ([_vp, _vp, _i32, C.POINTER(_i32), C.POINTER(_dbl), _vp, _dbl, _vp, _dbl, _dbl, _vp], C.c_int),
     "rbffd_rhs_advdiff_host": ([_vp, C.POINTER(AdvDiffParams), _vp, _vp], C.c_int),
     "rbffd_bc_create": ([_vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _i32, C.POINTER(_vp)], C.c_int),
     "rbffd_bc_apply_device": ([_vp, _vp], C.c_int),

@@ -58,7 +58,7 @@ def make_ops(dim, ops):
     return rows
 
 
-def make_options(dim, p, n, polydeg, ops, index_base=0, sort_columns=False, kernel=0, variant=0):
+def make_options(dim, p, n, polydeg, ops, index_base=0, sort_columns=False, kernel=0, variant=0, index_width=64):
     rows = make_ops(dim, ops)
     if not 1 <= len(rows) <= _lib.MAX_OPS:
         raise ValueError(f"between 1 and {_lib.MAX_OPS} operators per call")
@@ -69,6 +69,7 @@ def make_options(dim, p, n, polydeg, ops, index_base=0, sort_columns=False, kern
             o.ops[i][j] = r[j]
     o.index_base, o.sort_columns, o.kernel = int(index_base), int(bool(sort_columns)), int(kernel)
     o.variant = int(variant)
+    o.index_width = int(index_width)
     return o
 
 
@@ -173,6 +174,10 @@ class Context:
     def scatter_add_device(self, src_ptr, index_ptr, count, dst_ptr):
         self._check(self._L.rbffd_scatter_add_device(self._h, src_ptr, index_ptr, count, dst_ptr))
 
+    def stage_update_device(self, N, a, u_ptr, b, x_ptr, dt, du_ptr, out_ptr):
+        """out = a*u + b*(x + dt*du): the Shu-Osher stage combination of an SSP-RK scheme (element-wise; out may alias u or x)"""
+        self._check(self._L.rbffd_stage_update_device(self._h, N, a, u_ptr, b, x_ptr, dt, du_ptr, out_ptr))
+
 
 class Operator:
     """Device-resident operator set (shared sparsity pattern, fixed row length)."""
@@ -260,6 +265,16 @@ class Operator:
     def rhs_advdiff_device(self, u_ptr, du_ptr, params: AdvDiffParams):
         self.ctx._check(self.ctx._L.rbffd_rhs_advdiff_device(self._h, C.byref(params), u_ptr, du_ptr))
 
+    def rhs_advdiff_stage_device(self, x_ptr, a, u_ptr, b, dt, out_ptr, params: AdvDiffParams):
+        """out = a*u + b*(x + dt*cons_sys(x)) (ONE launch on the collocated path)"""
+        self.ctx._check(self.ctx._L.rbffd_rhs_advdiff_stage_device(self._h, C.byref(params), x_ptr, a, u_ptr, b, dt, out_ptr))
+
+    def spmv_stage_device(self, which, coef, x_ptr, a, u_ptr, b, dt, out_ptr):
+        """out = a*u + b*(x + dt * sum_i coef[i] D[which[i]] x): one SSP-RK stage as ONE launch (rows = nodes)"""
+        w = (C.c_int32 * len(which))(*which)
+        c = (C.c_double * len(coef))(*coef)
+        self.ctx._check(self.ctx._L.rbffd_spmv_stage_device(self._h, len(which), w, c, x_ptr, a, u_ptr, b, dt, out_ptr))
+
 
 class BoundaryConditions:
     """Ghost-node updates of cons_sys (examples/adv_diff_test.jl:118-141,162-176), device resident.
@@ -309,6 +324,48 @@ class BoundaryConditions:
 _default_ctx = None
 
 
+def bind_to_gpu_numa(device: int = 0) -> int:
+    """Restrict this process to the CPU cores next to GPU `device` (NVML's CPU affinity of the device, intersected with the
+    current mask): pinned staging buffers are then first-touched on that NUMA node and the widening threads of
+    rbffd_generate_operator_host stay next to the PCIe root they drain.  One process per GPU: call it before creating the
+    Context.  Returns the number of hardware threads left to the process (0: NVML unavailable, nothing changed)."""
+    import os
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+        idx = int(visible.split(",")[device]) if visible and all(t.strip().isdigit() for t in visible.split(",")) else device
+        h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return 0
+        # one process per GPU: the ranks that share this NUMA node split its cores between them
+        lw = int(os.environ.get("LOCAL_WORLD_SIZE", "1"))
+        lr = int(os.environ.get("LOCAL_RANK", "0"))
+        if lw > 1:
+            same = []
+            for r in range(lw):
+                try:
+                    hr = pynvml.nvmlDeviceGetHandleByIndex(int(visible.split(",")[r]) if visible and all(t.strip().isdigit() for t in visible.split(",")) else r)
+                    wr = pynvml.nvmlDeviceGetCpuAffinity(hr, (ncpu + 63) // 64)
+                    if list(wr) == list(words):
+                        same.append(r)
+                except Exception:
+                    pass
+            if lr in same and len(same) > 1:
+                order = sorted(cpus)
+                share = [c for i, c in enumerate(order) if i % len(same) == same.index(lr)]
+                if share:
+                    cpus = set(share)
+        os.sched_setaffinity(0, cpus)
+        return len(cpus)
+    except Exception:
+        return 0
+
+
 def default_context() -> Context:
     global _default_ctx
     if _default_ctx is None:
@@ -325,9 +382,9 @@ def _to_csc(colind, vals, shape_mode, N):
 
 
 def generate_raw(X, Y, p, n, polydeg, ops=REFERENCE_OPS, groups=None, ctx=None, sort_columns=False, kernel=0, variant=0,
-                 index_base=0):
-    """colind [M, n] int64 (stencil order unless sort_columns; index_base 0, or 1 as the Julia shim asks for),
-    vals [nops, M, n]: the fixed-row CSR the kernels write."""
+                 index_base=0, index_width=64):
+    """colind [M, n] int64 (int32 with index_width=32; stencil order unless sort_columns; index_base 0, or 1 as the Julia shim
+    asks for), vals [nops, M, n]: the fixed-row CSR the kernels write."""
     ctx = ctx or default_context()
     X = _coords(X, "X")
     Y = X if Y is None else _coords(Y, "Y")
@@ -335,8 +392,8 @@ def generate_raw(X, Y, p, n, polydeg, ops=REFERENCE_OPS, groups=None, ctx=None, 
         raise ValueError("DimensionMismatch: X and Y have different dimensions")
     N, dim = X.shape
     M = Y.shape[0]
-    opts = make_options(dim, p, n, polydeg, ops, index_base, sort_columns, kernel, variant)
-    colind = np.empty((M, n), np.int64)
+    opts = make_options(dim, p, n, polydeg, ops, index_base, sort_columns, kernel, variant, index_width)
+    colind = np.empty((M, n), np.int32 if index_width == 32 else np.int64)
     vals = np.empty((opts.nops, M, n), np.float64)
     g = None if groups is None else np.ascontiguousarray(groups, np.int32)
     if g is not None and g.shape != (N,):

@@ -7,12 +7,15 @@
 #include <cstdlib>
 #include <thread>
 #include <emmintrin.h>
+#include <sched.h>
 
 #include "common.cuh"
 
 int rbffd_spmv_multi_impl(rbffd_operator* op, int nterms, const int32_t* which, const double* coef, const double* x,
                           double beta, double* y);
 int rbffd_spmv_t_impl(rbffd_operator* op, int which, double alpha, const double* v, double beta, double* y);
+int rbffd_spmv_stage_impl(rbffd_operator* op, int nterms, const int32_t* which, const double* coef, const double* x,
+                          double a, const double* u, double b, double dt, double* out);
 int rbffd_gather_impl(rbffd_context* ctx, const double* src, const int32_t* index, int64_t count, double* dst);
 int rbffd_scatter_add_impl(rbffd_context* ctx, const double* src, const int32_t* index, int64_t count, double* dst);
 
@@ -23,6 +26,11 @@ thread_local std::string g_err_noctx;
 __global__ void i32_to_i64_kernel(const int32_t* __restrict__ in, int64_t n, int64_t base, int64_t* __restrict__ out) {
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i < n) out[i] = (int64_t)in[i] + base;
+}
+
+__global__ void i32_add_base_kernel(const int32_t* __restrict__ in, int64_t n, int32_t base, int32_t* __restrict__ out) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) out[i] = in[i] + base;
 }
 
 __global__ void i64_to_i32_kernel(const int64_t* __restrict__ in, int64_t n, int64_t base, int32_t* __restrict__ out, int64_t hi, int* bad) {
@@ -347,11 +355,23 @@ int rbffd_generate_operator_host(rbffd_context* ctx, const rbffd_options* opts, 
         const char* lw_env = getenv("LOCAL_WORLD_SIZE");            // one process per GPU: share the host cores
         const unsigned hc = std::thread::hardware_concurrency();
         const unsigned lw = lw_env ? (unsigned)std::max(1, atoi(lw_env)) : 1u;
-        const int T = wt_env ? std::max(1, atoi(wt_env)) : (int)std::min(8u, hc / (2 * lw));
+        // hardware threads THIS process may use: its affinity mask when the launcher bound it to the cores next to its GPU
+        // (rb.bind_to_gpu_numa), else an equal share of the host
+        unsigned avail = hc / lw;
+        {
+            cpu_set_t set;
+            CPU_ZERO(&set);
+            if (sched_getaffinity(0, sizeof(set), &set) == 0) {
+                const unsigned bound = (unsigned)CPU_COUNT(&set);
+                if (bound > 0 && bound < hc) avail = bound;
+            }
+        }
+        const int T = wt_env ? std::max(1, atoi(wt_env)) : (int)std::max(1u, std::min(8u, avail / 2));
         // Several ranks on one host share its ingest bandwidth (measured at N = 2: 16.3 ms per call when every rank ships the
-        // int64 pattern, 11.1 ms with the int32 pattern widened by 6 host threads per rank), so the smaller transfer stays the
-        // default as long as every rank gets at least 4 widening threads.
-        bool host_widen = hw_env ? atoi(hw_env) != 0 : T >= 4;
+        // int64 pattern, 11.1 ms with the int32 pattern widened by 6 host threads per rank), so the int32 transfer is the
+        // default at any rank count: the widening threads are capped by the cores of the rank, never replaced by an int64 copy.
+        const bool want32 = opts->index_width == 32;
+        bool host_widen = !want32 && (hw_env ? atoi(hw_env) != 0 : true);
         constexpr int NSL = 8;
         struct Wideners {                          // joined on every exit path (the threads only wait for queued copies)
             std::vector<std::thread> th;
@@ -375,7 +395,20 @@ int rbffd_generate_operator_host(rbffd_context* ctx, const rbffd_options* opts, 
             if (cudaHostAlloc(&ctx->stage_i32, sizeof(int32_t) * (size_t)total, cudaHostAllocDefault) == cudaSuccess) ctx->stage_i32_count = (size_t)total;
             else { cudaGetLastError(); ctx->stage_i32 = nullptr; host_widen = false; }     // no pinned memory left: widen on the device
         }
-        if (host_widen) {
+        DevBuf<int32_t> c32b;
+        if (want32) {
+            // the caller keeps int32 indices (SparseMatrixCSC{Float64,Int32}): the stencils go straight into its buffer
+            const int32_t* srcp = stencils.p;
+            if (opts->index_base != 0) {
+                CUDA_TRY(ctx, c32b.alloc((size_t)total, st));
+                i32_add_base_kernel<<<ceil_div_i64(total, 256), 256, 0, st>>>(stencils.p, total, opts->index_base, c32b.p);
+                KLAUNCH(ctx);
+                srcp = c32b.p;
+            }
+            CUDA_TRY(ctx, cudaEventRecord(ctx->chunk_ev[2], st));
+            CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->chunk_ev[2], 0));
+            CUDA_TRY(ctx, cudaMemcpyAsync(reinterpret_cast<int32_t*>(colind_out), srcp, sizeof(int32_t) * (size_t)total, cudaMemcpyDeviceToHost, ctx->copy_stream));
+        } else if (host_widen) {
             CUDA_TRY(ctx, cudaEventRecord(ctx->chunk_ev[2], st));
             CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->chunk_ev[2], 0));
             const int64_t sl = ((total + NSL - 1) / NSL + 63) / 64 * 64;
@@ -484,7 +517,22 @@ int rbffd_generate_operator_host(rbffd_context* ctx, const rbffd_options* opts, 
     }
     rbffd_operator* op = nullptr;
     RBFFD_TRY(rbffd_operator_generate(ctx, opts, dX.p, N, dYp, M, xgroup ? dG.p : nullptr, &op));
-    int rc = rbffd_operator_to_host(op, opts->index_base, colind_out, vals_out);
+    int rc = RBFFD_OK;
+    if (opts->index_width == 32) {
+        const int64_t nnz = op->M * op->n;
+        DevBuf<int32_t> tmp;
+        cudaError_t e = tmp.alloc((size_t)std::max<int64_t>(nnz, 1), st);
+        if (e == cudaSuccess && nnz > 0) {
+            i32_add_base_kernel<<<ceil_div_i64(nnz, 256), 256, 0, st>>>(op->colind, nnz, opts->index_base, tmp.p);
+            KLAUNCH(ctx);
+            e = cudaMemcpyAsync(reinterpret_cast<int32_t*>(colind_out), tmp.p, sizeof(int32_t) * (size_t)nnz, cudaMemcpyDeviceToHost, st);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(vals_out, op->vals, sizeof(double) * (size_t)nnz * op->nmat, cudaMemcpyDeviceToHost, st);
+        }
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) { ctx->err = std::string("CUDA error in generate_operator (int32 output): ") + cudaGetErrorString(e); rc = RBFFD_ERR_CUDA; }
+    } else {
+        rc = rbffd_operator_to_host(op, opts->index_base, colind_out, vals_out);
+    }
     rbffd_operator_destroy(op);
     return rc;
 }
@@ -553,7 +601,7 @@ int rbffd_operator_destroy(rbffd_operator* op) {
     if (!op) return RBFFD_OK;
     if (op->ctx) { cudaSetDevice(op->ctx->device); cudaStreamSynchronize(op->ctx->stream); }
     if (!op->borrowed) { cudaFree(op->colind); cudaFree(op->vals); }
-    cudaFree(op->t_ptr); cudaFree(op->t_src); cudaFree(op->t_row); cudaFree(op->work);
+    cudaFree(op->t_ptr); cudaFree(op->t_src); cudaFree(op->t_row); cudaFree(op->work); cudaFree(op->work2);
     for (double* p : op->t_vals) cudaFree(p);
     delete op;
     return RBFFD_OK;
@@ -687,12 +735,82 @@ int rbffd_spmv_t_host(rbffd_operator* op, int32_t which, double alpha, const dou
     }, &a);
 }
 
+namespace {
+// max |E - I| over the entries of one value plane (rows = nodes): decides whether E' * w may be replaced by w
+__global__ void identity_defect_kernel(const int32_t* __restrict__ colind, const double* __restrict__ vals, int64_t M, int n, unsigned long long* out) {
+    const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    double d = 0.0;
+    if (e < M * n) {
+        const int64_t row = e / n;
+        const double v = vals[e] - (colind[e] == row ? 1.0 : 0.0);
+        d = v == v ? fabs(v) : __longlong_as_double(0x7ff0000000000000ll);
+    }
+    for (int o = 16; o > 0; o >>= 1) d = fmax(d, __shfl_xor_sync(0xffffffffu, d, o));
+    if ((threadIdx.x & 31) == 0 && d > 0.0) atomicMax(out, (unsigned long long)__double_as_longlong(d));     // non-negative doubles order like integers
+}
+
+// 1: matrix iE of a square operator equals the identity to 1e-8: at collocated rows E = I exactly, what the weight solve returns
+// deviates from it by its rounding noise only (eps * cond(A_i): 1e-11 ... 1e-9 at the configurations of BASELINE.json)
+int e_is_identity(rbffd_operator* op, int iE, bool* yes) {
+    rbffd_context* ctx = op->ctx;
+    *yes = false;
+    if (op->M != op->N || iE < 0 || iE >= op->nmat) return RBFFD_OK;
+    if (op->e_identity_which == iE && op->e_identity >= 0) { *yes = op->e_identity == 1; return RBFFD_OK; }
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    CUDA_TRY(ctx, cudaStreamIsCapturing(ctx->stream, &cap));
+    if (cap != cudaStreamCaptureStatusNone) return RBFFD_OK;            // cannot synchronise inside a capture: take the general path
+    DevBuf<unsigned long long> d;
+    CUDA_TRY(ctx, d.alloc(1, ctx->stream));
+    CUDA_TRY(ctx, cudaMemsetAsync(d.p, 0, sizeof(unsigned long long), ctx->stream));
+    const int64_t nnz = op->M * (int64_t)op->n;
+    identity_defect_kernel<<<ceil_div_i64(std::max<int64_t>(nnz, 1), 256), 256, 0, ctx->stream>>>(op->colind, op->vals + (size_t)nnz * iE, op->M, op->n, d.p);
+    KLAUNCH(ctx);
+    unsigned long long h = 0;
+    CUDA_TRY(ctx, cudaMemcpyAsync(&h, d.p, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    double defect;
+    memcpy(&defect, &h, sizeof(defect));
+    op->e_identity_which = iE;
+    op->e_identity = defect <= 1e-8 ? 1 : 0;
+    *yes = op->e_identity == 1;
+    return RBFFD_OK;
+}
+
+// terms of the interior line of cons_sys with E = I: alpha*(Dxx + Dyy) - ux*Dx - uy*Dy - gamma*(Dxk + Dyk); zero coefficients dropped
+int advdiff_terms(const rbffd_advdiff_params* prm, int32_t* which, double* coef) {
+    int nt = 0;
+    if (prm->alpha != 0.0) { which[nt] = prm->iDxx; coef[nt++] = prm->alpha; which[nt] = prm->iDyy; coef[nt++] = prm->alpha; }
+    if (prm->ux != 0.0) { which[nt] = prm->iDx; coef[nt++] = -prm->ux; }
+    if (prm->uy != 0.0) { which[nt] = prm->iDy; coef[nt++] = -prm->uy; }
+    if (prm->iDxk >= 0 && prm->iDyk >= 0 && prm->gamma != 0.0) { which[nt] = prm->iDxk; coef[nt++] = -prm->gamma; which[nt] = prm->iDyk; coef[nt++] = -prm->gamma; }
+    return nt;
+}
+
+// element-wise, so out may alias u or x
+__global__ void stage_update_kernel(int64_t N, double a, const double* u, double b, const double* x, double dt, const double* du, double* out) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < N) out[i] = a * u[i] + b * (x[i] + dt * du[i]);
+}
+}  // namespace
+
 int rbffd_rhs_advdiff_device(rbffd_operator* op, const rbffd_advdiff_params* prm, const double* u, double* du) {
     if (!op) return RBFFD_ERR_INVALID;
     rbffd_context* ctx = op->ctx;
     if (!prm || !u || !du) RBFFD_FAIL(ctx, RBFFD_ERR_INVALID, "rhs_advdiff: NULL pointer");
     if (op->M != op->N) RBFFD_FAIL(ctx, RBFFD_ERR_INVALID, "rhs_advdiff: the semidiscretisation needs square operators (M == N)");
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    if (prm->flags & RBFFD_ADVDIFF_COLLOCATED) {
+        // collocated rows: E = I, so the whole line is ONE pass over the shared pattern with up to six value planes
+        bool ident = false;
+        RBFFD_TRY(e_is_identity(op, prm->iE, &ident));
+        if (ident) {
+            int32_t which[6];
+            double coef[6];
+            const int nt = advdiff_terms(prm, which, coef);
+            if (nt == 0) { CUDA_TRY(ctx, cudaMemsetAsync(du, 0, sizeof(double) * op->N, ctx->stream)); return RBFFD_OK; }
+            return rbffd_spmv_multi_impl(op, nt, which, coef, u, 0.0, du);
+        }
+    }
     if (!op->work) CUDA_TRY(ctx, cudaMalloc((void**)&op->work, sizeof(double) * (size_t)std::max<int64_t>(op->M, 1)));
     // w = alpha*Dxx*u + alpha*Dyy*u - ux*Dx*u - uy*Dy*u  (zero coefficients are dropped: no traffic for them)
     int32_t which[4];
@@ -711,6 +829,50 @@ int rbffd_rhs_advdiff_device(rbffd_operator* op, const rbffd_advdiff_params* prm
         double ck[2] = {-prm->gamma, -prm->gamma};
         RBFFD_TRY(rbffd_spmv_multi_impl(op, 2, wk, ck, u, 1.0, du));
     }
+    return RBFFD_OK;
+}
+
+int rbffd_spmv_stage_device(rbffd_operator* op, int32_t nterms, const int32_t* which, const double* coef, const double* x,
+                            double a, const double* u, double b, double dt, double* out) {
+    if (!op) return RBFFD_ERR_INVALID;
+    if (!which || !coef || !x || !u || !out) RBFFD_FAIL(op->ctx, RBFFD_ERR_INVALID, "spmv_stage: NULL pointer");
+    CUDA_TRY(op->ctx, cudaSetDevice(op->ctx->device));
+    return rbffd_spmv_stage_impl(op, nterms, which, coef, x, a, u, b, dt, out);
+}
+
+int rbffd_rhs_advdiff_stage_device(rbffd_operator* op, const rbffd_advdiff_params* prm, const double* x, double a, const double* u,
+                                   double b, double dt, double* out) {
+    if (!op) return RBFFD_ERR_INVALID;
+    rbffd_context* ctx = op->ctx;
+    if (!prm || !x || !u || !out) RBFFD_FAIL(ctx, RBFFD_ERR_INVALID, "rhs_advdiff_stage: NULL pointer");
+    if (op->M != op->N) RBFFD_FAIL(ctx, RBFFD_ERR_INVALID, "rhs_advdiff_stage: the semidiscretisation needs square operators (M == N)");
+    if (out == x || out == u) RBFFD_FAIL(ctx, RBFFD_ERR_INVALID, "rhs_advdiff_stage: out must not alias x or u");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    if (prm->flags & RBFFD_ADVDIFF_COLLOCATED) {
+        bool ident = false;
+        RBFFD_TRY(e_is_identity(op, prm->iE, &ident));
+        int32_t which[6];
+        double coef[6];
+        const int nt = advdiff_terms(prm, which, coef);
+        if (ident && nt > 0) return rbffd_spmv_stage_impl(op, nt, which, coef, x, a, u, b, dt, out);
+    }
+    if (!op->work2) CUDA_TRY(ctx, cudaMalloc((void**)&op->work2, sizeof(double) * (size_t)std::max<int64_t>(op->N, 1)));
+    RBFFD_TRY(rbffd_rhs_advdiff_device(op, prm, x, op->work2));
+    stage_update_kernel<<<ceil_div_i64(std::max<int64_t>(op->N, 1), 256), 256, 0, ctx->stream>>>(op->N, a, u, b, x, dt, op->work2, out);
+    KLAUNCH(ctx);
+    CUDA_TRY(ctx, cudaGetLastError());
+    return RBFFD_OK;
+}
+
+int rbffd_stage_update_device(rbffd_context* ctx, int64_t N, double a, const double* u, double b, const double* x, double dt,
+                              const double* du, double* out) {
+    if (!ctx) return RBFFD_ERR_INVALID;
+    if (N < 0 || !u || !x || !du || !out) RBFFD_FAIL(ctx, RBFFD_ERR_INVALID, "stage_update: bad arguments");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    if (N == 0) return RBFFD_OK;
+    stage_update_kernel<<<ceil_div_i64(N, 256), 256, 0, ctx->stream>>>(N, a, u, b, x, dt, du, out);
+    KLAUNCH(ctx);
+    CUDA_TRY(ctx, cudaGetLastError());
     return RBFFD_OK;
 }
 

@@ -8,6 +8,7 @@
 // reference does with inv(Array(w_bc_g))).  The per-call part runs on the device: one masked row product per
 // boundary node straight from the fixed-row CSR (no sliced copies), then one small dense GEMV.
 #include <cmath>
+#include <cstdlib>
 #include <new>
 #include <vector>
 
@@ -60,6 +61,52 @@ __global__ void bc_solve_kernel(int nbc, const double* __restrict__ winv, const 
 __global__ void bc_set_kernel(int nbc, const int32_t* __restrict__ a, const int32_t* __restrict__ b, double value, double* __restrict__ u) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < nbc) { u[a[i]] = value; u[b[i]] = value; }
+}
+
+// All boundaries in ONE launch (one CTA): the boundaries depend on each other through corner stencils, so they run one after
+// the other inside the CTA with block-wide barriers in between; per boundary the arithmetic is that of bc_rows_kernel /
+// bc_solve_kernel (one warp per boundary node, lanes stride 32), so the result is bit-identical to the launch-per-kernel path.
+constexpr int BC_FUSED_MAX_B = 16, BC_FUSED_MAX_NBC = 1024, BC_FUSED_THREADS = 512;
+struct BcFused {
+    int nb;
+    int kind[BC_FUSED_MAX_B], cnt[BC_FUSED_MAX_B], off[BC_FUSED_MAX_B];
+    const double* vals[BC_FUSED_MAX_B];
+    const double* winv[BC_FUSED_MAX_B];
+    double value[BC_FUSED_MAX_B];
+};
+__global__ void __launch_bounds__(BC_FUSED_THREADS) bc_fused_kernel(BcFused f, int n, const int32_t* __restrict__ bc_idx, const int32_t* __restrict__ ghost_idx,
+                                                                    const int32_t* __restrict__ colind, const int8_t* __restrict__ ghost_of, double* u) {
+    __shared__ double t[BC_FUSED_MAX_NBC];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = BC_FUSED_THREADS / 32;
+    for (int b = 0; b < f.nb; ++b) {
+        const int cnt = f.cnt[b];
+        const int32_t* rows = bc_idx + f.off[b];
+        const int32_t* gh = ghost_idx + f.off[b];
+        if (f.kind[b] == 1) {
+            const double* vals = f.vals[b];
+            for (int i = warp; i < cnt; i += nwarps) {
+                const int64_t base = (int64_t)rows[i] * n;
+                double acc = 0.0;
+                for (int j = lane; j < n; j += 32) {
+                    const int c = colind[base + j];
+                    if (ghost_of[c] != b + 1) acc += vals[base + j] * u[c];
+                }
+                for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+                if (lane == 0) t[i] = acc;
+            }
+            __syncthreads();
+            const double* winv = f.winv[b];
+            for (int i = warp; i < cnt; i += nwarps) {
+                double acc = 0.0;
+                for (int k = lane; k < cnt; k += 32) acc += winv[(size_t)i * cnt + k] * t[k];
+                for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+                if (lane == 0) u[gh[i]] = -acc;
+            }
+        } else {
+            for (int i = threadIdx.x; i < cnt; i += BC_FUSED_THREADS) { u[rows[i]] = f.value[b]; u[gh[i]] = f.value[b]; }
+        }
+        __syncthreads();             // this boundary's ghost values are visible to the next one (same CTA: no fence needed beyond the barrier)
+    }
 }
 
 // dense inverse by Gauss-Jordan with partial pivoting (host, cold path); returns false if singular
@@ -176,6 +223,22 @@ int rbffd_bc_apply_device(rbffd_bc* bc, double* u) {
     if (!u) RBFFD_FAIL(ctx, RBFFD_ERR_INVALID, "bc_apply: NULL pointer");
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
+    int maxn = 0;
+    for (int b = 0; b < bc->nb; ++b) maxn = std::max(maxn, bc->nbc[b]);
+    static const bool no_fuse = [] { const char* e = getenv("RBFFD_BC_FUSED"); return e && atoi(e) == 0; }();
+    if (bc->nb <= BC_FUSED_MAX_B && maxn <= BC_FUSED_MAX_NBC && !no_fuse) {
+        BcFused f{};
+        f.nb = bc->nb;
+        for (int b = 0; b < bc->nb; ++b) {
+            f.kind[b] = bc->kind[b]; f.cnt[b] = bc->nbc[b]; f.off[b] = bc->off[b]; f.value[b] = bc->value[b];
+            f.vals[b] = bc->kind[b] == 1 ? op->vals + (size_t)op->M * op->n * bc->which[b] : nullptr;
+            f.winv[b] = bc->winv + bc->winv_off[b];
+        }
+        bc_fused_kernel<<<1, BC_FUSED_THREADS, 0, st>>>(f, op->n, bc->bc_idx, bc->ghost_idx, op->colind, bc->ghost_of, u);
+        KLAUNCH(ctx);
+        CUDA_TRY(ctx, cudaGetLastError());
+        return RBFFD_OK;
+    }
     for (int b = 0; b < bc->nb; ++b) {
         const int cnt = bc->nbc[b];
         if (cnt == 0) continue;

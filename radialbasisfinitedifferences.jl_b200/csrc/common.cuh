@@ -46,6 +46,8 @@ struct rbffd_operator {
     std::vector<double*> t_vals; // [nmat] values in column order, built on the first E'*v of a matrix (owned operators only:
                                  // a borrowed operator's values may be rewritten by the caller between applications)
     double* work = nullptr;      // [M] scratch
+    double* work2 = nullptr;     // [N] scratch of the unfused stage path
+    int e_identity = -1, e_identity_which = -1;   // cached answer of "is matrix e_identity_which the identity (1e-12)?"
     bool borrowed = false;       // colind/vals belong to the caller (rbffd_operator_from_device)
 };
 

@@ -80,11 +80,8 @@ __device__ __forceinline__ void spin_until(const unsigned* flag, unsigned value)
 // grid = [PB push CTAs | IB interior-row CTAs | BB boundary-row CTAs]; MODE 0 = fused exchange, 1 = no exchange (inbox filled
 // by rbffd_shard_unpack_device)
 template <int TPR, int NMAT, int VEC, int ITERS, int MODE>
-__global__ void __launch_bounds__(256) shard_spmv_kernel(ShardDev sd, int n, const int32_t* __restrict__ colind,
-                                                         const double* __restrict__ v0, const double* __restrict__ v1,
-                                                         const double* __restrict__ v2, const double* __restrict__ v3,
-                                                         double c0, double c1, double c2, double c3,
-                                                         const double* __restrict__ x, double* __restrict__ y, int PB, int IB) {
+__global__ void __launch_bounds__(256) shard_spmv_kernel(ShardDev sd, int n, const int32_t* __restrict__ colind, SpmvMats m,
+                                                         const double* __restrict__ x, SpmvEpilogue epi, double* __restrict__ y, int PB, int IB) {
     __shared__ unsigned s_epoch;
     if (MODE == 0) {
         if (threadIdx.x == 0) s_epoch = *reinterpret_cast<volatile unsigned*>(&sd.ctl->epoch) + 1u;
@@ -114,15 +111,14 @@ __global__ void __launch_bounds__(256) shard_spmv_kernel(ShardDev sd, int n, con
         }
     } else if (b < PB + IB) {
         const int64_t warp = ((int64_t)(b - PB) * 256 + threadIdx.x) >> 5;
-        spmv_rows<TPR, NMAT, VEC, ITERS, false>(warp, 0, sd.n_int, n, colind, v0, v1, v2, v3, c0, c1, c2, c3, x, nullptr, 0, 0.0, y);
+        spmv_rows<TPR, NMAT, VEC, ITERS, false>(warp, 0, sd.n_int, n, colind, m, x, nullptr, 0, epi, y);
     } else {
         if (MODE == 0) {
             if ((int)threadIdx.x < sd.nrecv) spin_until(sd.flags + F_READY + sd.recv_peer[threadIdx.x], ep);
             __syncthreads();
         }
         const int64_t warp = ((int64_t)(b - PB - IB) * 256 + threadIdx.x) >> 5;
-        spmv_rows<TPR, NMAT, VEC, ITERS, true>(warp, sd.n_int, sd.n_owned, n, colind, v0, v1, v2, v3, c0, c1, c2, c3, x, sd.inbox,
-                                               (int)sd.n_owned, 0.0, y);
+        spmv_rows<TPR, NMAT, VEC, ITERS, true>(warp, sd.n_int, sd.n_owned, n, colind, m, x, sd.inbox, (int)sd.n_owned, epi, y);
         if (MODE == 0) {
             __syncthreads();                       // every halo value this CTA needs has been read
             if (threadIdx.x == 0) {
@@ -352,7 +348,7 @@ int ensure_gid_host(rbffd_shard* s) {
 }
 
 template <int TPR, int VEC, int ITERS, int MODE>
-int launch_shard(rbffd_shard* s, rbffd_operator* op, int nm, const double* const* v, const double* c, const double* x, double* y) {
+int launch_shard(rbffd_shard* s, rbffd_operator* op, int nm, const SpmvMats& m, const double* x, const SpmvEpilogue& ep, double* y) {
     rbffd_context* ctx = s->ctx;
     const int rows_per_block = 256 / TPR;
     const int PB = MODE == 0 ? s->dev.chunk_off[s->dev.nsend] : 0;
@@ -362,10 +358,12 @@ int launch_shard(rbffd_shard* s, rbffd_operator* op, int nm, const double* const
     if (grid == 0) return RBFFD_OK;
     cudaStream_t st = ctx->stream;
     switch (nm) {
-        case 1: shard_spmv_kernel<TPR, 1, VEC, ITERS, MODE><<<grid, 256, 0, st>>>(s->dev, op->n, op->colind, v[0], v[0], v[0], v[0], c[0], 0, 0, 0, x, y, PB, IB); break;
-        case 2: shard_spmv_kernel<TPR, 2, VEC, ITERS, MODE><<<grid, 256, 0, st>>>(s->dev, op->n, op->colind, v[0], v[1], v[0], v[0], c[0], c[1], 0, 0, x, y, PB, IB); break;
-        case 3: shard_spmv_kernel<TPR, 3, VEC, ITERS, MODE><<<grid, 256, 0, st>>>(s->dev, op->n, op->colind, v[0], v[1], v[2], v[0], c[0], c[1], c[2], 0, x, y, PB, IB); break;
-        default: shard_spmv_kernel<TPR, 4, VEC, ITERS, MODE><<<grid, 256, 0, st>>>(s->dev, op->n, op->colind, v[0], v[1], v[2], v[3], c[0], c[1], c[2], c[3], x, y, PB, IB); break;
+        case 1: shard_spmv_kernel<TPR, 1, VEC, ITERS, MODE><<<grid, 256, 0, st>>>(s->dev, op->n, op->colind, m, x, ep, y, PB, IB); break;
+        case 2: shard_spmv_kernel<TPR, 2, VEC, ITERS, MODE><<<grid, 256, 0, st>>>(s->dev, op->n, op->colind, m, x, ep, y, PB, IB); break;
+        case 3: shard_spmv_kernel<TPR, 3, VEC, ITERS, MODE><<<grid, 256, 0, st>>>(s->dev, op->n, op->colind, m, x, ep, y, PB, IB); break;
+        case 4: shard_spmv_kernel<TPR, 4, VEC, ITERS, MODE><<<grid, 256, 0, st>>>(s->dev, op->n, op->colind, m, x, ep, y, PB, IB); break;
+        case 5: shard_spmv_kernel<TPR, 5, VEC, ITERS, MODE><<<grid, 256, 0, st>>>(s->dev, op->n, op->colind, m, x, ep, y, PB, IB); break;
+        default: shard_spmv_kernel<TPR, 6, VEC, ITERS, MODE><<<grid, 256, 0, st>>>(s->dev, op->n, op->colind, m, x, ep, y, PB, IB); break;
     }
     KLAUNCH(ctx);
     CUDA_TRY(ctx, cudaGetLastError());
@@ -373,35 +371,36 @@ int launch_shard(rbffd_shard* s, rbffd_operator* op, int nm, const double* const
 }
 
 template <int MODE>
-int dispatch_shard(rbffd_shard* s, rbffd_operator* op, int nterms, const int32_t* which, const double* coef, const double* x, double* y) {
+int dispatch_shard(rbffd_shard* s, rbffd_operator* op, int nterms, const int32_t* which, const double* coef, const double* x,
+                   const SpmvEpilogue& ep, double* y) {
     rbffd_context* ctx = s->ctx;
     if (!op || !which || !coef || !x || !y) RBFFD_FAIL(ctx, RBFFD_ERR_INVALID, "shard_spmv: NULL argument");
-    if (nterms < 1 || nterms > 4) RBFFD_FAIL(ctx, RBFFD_ERR_INVALID, "shard_spmv: 1..4 terms per launch (combine the operators first: rbffd_operator_combine_device)");
+    if (nterms < 1 || nterms > SPMV_MAXMAT) RBFFD_FAIL(ctx, RBFFD_ERR_INVALID, "shard_spmv: 1..%d terms per launch (combine the operators first: rbffd_operator_combine_device)", SPMV_MAXMAT);
     if (op->M != s->n_owned || op->N != s->n_owned + s->n_halo)
         RBFFD_FAIL(ctx, RBFFD_ERR_INVALID, "shard_spmv: operator is %lld x %lld, the shard needs %lld x %lld", (long long)op->M, (long long)op->N,
                    (long long)s->n_owned, (long long)(s->n_owned + s->n_halo));
     if (MODE == 0 && !s->finalized) RBFFD_FAIL(ctx, RBFFD_ERR_INVALID, "shard_spmv: rbffd_shard_finalize / _connect have not run");
-    const double* v[4];
-    double c[4];
+    if (ep.su && (y == x || y == ep.su)) RBFFD_FAIL(ctx, RBFFD_ERR_INVALID, "shard_spmv_stage: out must not alias x or u");
+    SpmvMats m{};
     const size_t stride = (size_t)op->M * op->n;
     for (int i = 0; i < nterms; ++i) {
         if (which[i] < 0 || which[i] >= op->nmat) RBFFD_FAIL(ctx, RBFFD_ERR_INVALID, "shard_spmv: matrix index %d out of range", which[i]);
-        v[i] = op->vals + stride * which[i];
-        c[i] = coef[i];
+        m.v[i] = op->vals + stride * which[i];
+        m.c[i] = coef[i];
     }
     const int n = op->n;
     bool even = (n % 2) == 0 && reinterpret_cast<uintptr_t>(op->colind) % 8 == 0;
-    for (int i = 0; i < nterms; ++i) even = even && reinterpret_cast<uintptr_t>(v[i]) % 16 == 0;
+    for (int i = 0; i < nterms; ++i) even = even && reinterpret_cast<uintptr_t>(m.v[i]) % 16 == 0;
     if (even) {
-        if (n <= 16) return launch_shard<4, 2, 2, MODE>(s, op, nterms, v, c, x, y);
-        if (n <= 32) return launch_shard<8, 2, 2, MODE>(s, op, nterms, v, c, x, y);
-        if (n <= 48) return launch_shard<8, 2, 3, MODE>(s, op, nterms, v, c, x, y);
-        if (n <= 64) return launch_shard<8, 2, 4, MODE>(s, op, nterms, v, c, x, y);
-        if (n <= 128) return launch_shard<16, 2, 4, MODE>(s, op, nterms, v, c, x, y);
+        if (n <= 16) return launch_shard<4, 2, 2, MODE>(s, op, nterms, m, x, ep, y);
+        if (n <= 32) return launch_shard<8, 2, 2, MODE>(s, op, nterms, m, x, ep, y);
+        if (n <= 48) return launch_shard<8, 2, 3, MODE>(s, op, nterms, m, x, ep, y);
+        if (n <= 64) return launch_shard<8, 2, 4, MODE>(s, op, nterms, m, x, ep, y);
+        if (n <= 128) return launch_shard<16, 2, 4, MODE>(s, op, nterms, m, x, ep, y);
     } else {
-        if (n <= 32) return launch_shard<8, 1, 4, MODE>(s, op, nterms, v, c, x, y);
-        if (n <= 64) return launch_shard<8, 1, 8, MODE>(s, op, nterms, v, c, x, y);
-        if (n <= 128) return launch_shard<16, 1, 8, MODE>(s, op, nterms, v, c, x, y);
+        if (n <= 32) return launch_shard<8, 1, 4, MODE>(s, op, nterms, m, x, ep, y);
+        if (n <= 64) return launch_shard<8, 1, 8, MODE>(s, op, nterms, m, x, ep, y);
+        if (n <= 128) return launch_shard<16, 1, 8, MODE>(s, op, nterms, m, x, ep, y);
     }
     RBFFD_FAIL(ctx, RBFFD_ERR_UNSUPPORTED, "shard_spmv: row length %d > 128", n);
 }
@@ -830,7 +829,22 @@ int rbffd_shard_spmv_device(rbffd_shard* s, rbffd_operator* op, int32_t nterms, 
         if (!d.send_dst[k] || !d.send_flags[k]) RBFFD_FAIL(s->ctx, RBFFD_ERR_INVALID, "shard_spmv: peer %d is not connected", d.send_peer[k]);
     for (int r = 0; r < d.nrecv; ++r)
         if (!d.recv_flags[r]) RBFFD_FAIL(s->ctx, RBFFD_ERR_INVALID, "shard_spmv: peer %d is not connected", d.recv_peer[r]);
-    return dispatch_shard<0>(s, op, nterms, which, coef, x, y);
+    return dispatch_shard<0>(s, op, nterms, which, coef, x, SpmvEpilogue{0.0, nullptr, 0.0, 0.0, 0.0}, y);
+}
+
+// out[0:n_owned] = a * u + b * (x + dt * sum_i coef[i] * D[which[i]] * [x ; halo of x]): one SSP-RK stage of the sharded
+// semidiscretisation as ONE launch (halo exchange, product and stage update)
+int rbffd_shard_spmv_stage_device(rbffd_shard* s, rbffd_operator* op, int32_t nterms, const int32_t* which, const double* coef,
+                                  const double* x, double a, const double* u, double b, double dt, double* out) {
+    if (!s) return RBFFD_ERR_INVALID;
+    if (!u) RBFFD_FAIL(s->ctx, RBFFD_ERR_INVALID, "shard_spmv_stage: NULL argument");
+    CUDA_TRY(s->ctx, cudaSetDevice(s->ctx->device));
+    const ShardDev& d = s->dev;
+    for (int k = 0; k < d.nsend; ++k)
+        if (!d.send_dst[k] || !d.send_flags[k]) RBFFD_FAIL(s->ctx, RBFFD_ERR_INVALID, "shard_spmv_stage: peer %d is not connected", d.send_peer[k]);
+    for (int r = 0; r < d.nrecv; ++r)
+        if (!d.recv_flags[r]) RBFFD_FAIL(s->ctx, RBFFD_ERR_INVALID, "shard_spmv_stage: peer %d is not connected", d.recv_peer[r]);
+    return dispatch_shard<0>(s, op, nterms, which, coef, x, SpmvEpilogue{0.0, u, a, b, dt}, out);
 }
 
 int rbffd_shard_spmv_local_device(rbffd_shard* s, rbffd_operator* op, int32_t nterms, const int32_t* which, const double* coef, const double* x, double* y) {
@@ -846,7 +860,7 @@ int rbffd_shard_spmv_local_device(rbffd_shard* s, rbffd_operator* op, int32_t nt
         s->dev.n_int = s->n_int;
         s->dev.me = s->rank;
     }
-    return dispatch_shard<1>(s, op, nterms, which, coef, x, y);
+    return dispatch_shard<1>(s, op, nterms, which, coef, x, SpmvEpilogue{0.0, nullptr, 0.0, 0.0, 0.0}, y);
 }
 
 int rbffd_shard_pack_device(rbffd_shard* s, int32_t peer, const double* x, double* sendbuf) {

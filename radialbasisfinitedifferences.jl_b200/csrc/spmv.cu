@@ -14,13 +14,10 @@
 namespace {
 
 template <int TPR, int NMAT, int VEC, int ITERS>
-__global__ void __launch_bounds__(256) spmv_multi_kernel(int64_t M, int n, const int32_t* __restrict__ colind,
-                                                         const double* __restrict__ v0, const double* __restrict__ v1,
-                                                         const double* __restrict__ v2, const double* __restrict__ v3,
-                                                         double c0, double c1, double c2, double c3,
-                                                         const double* __restrict__ x, double beta, double* __restrict__ y) {
+__global__ void __launch_bounds__(256) spmv_multi_kernel(int64_t M, int n, const int32_t* __restrict__ colind, SpmvMats m,
+                                                         const double* __restrict__ x, SpmvEpilogue ep, double* __restrict__ y) {
     const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
-    spmv_rows<TPR, NMAT, VEC, ITERS, false>(warp, 0, M, n, colind, v0, v1, v2, v3, c0, c1, c2, c3, x, nullptr, 0, beta, y);
+    spmv_rows<TPR, NMAT, VEC, ITERS, false>(warp, 0, M, n, colind, m, x, nullptr, 0, ep, y);
 }
 
 // y[c] = alpha * sum_{entries e in column c} vals[e] * v[row(e)] + beta * y[c]: 8 lanes per column, entries of a column are
@@ -95,16 +92,18 @@ __global__ void scatter_add_kernel(const double* __restrict__ src, const int32_t
 }
 
 template <int TPR, int VEC, int ITERS>
-int launch_multi(rbffd_operator* op, int nm, const double* const* v, const double* c, const double* x, double beta, double* y) {
+int launch_multi(rbffd_operator* op, int nm, const SpmvMats& m, const double* x, const SpmvEpilogue& ep, double* y) {
     rbffd_context* ctx = op->ctx;
     const int rows_per_block = 256 / TPR;
     const int grid = ceil_div_i64(op->M, rows_per_block);
     cudaStream_t st = ctx->stream;
     switch (nm) {
-        case 1: spmv_multi_kernel<TPR, 1, VEC, ITERS><<<grid, 256, 0, st>>>(op->M, op->n, op->colind, v[0], v[0], v[0], v[0], c[0], 0, 0, 0, x, beta, y); break;
-        case 2: spmv_multi_kernel<TPR, 2, VEC, ITERS><<<grid, 256, 0, st>>>(op->M, op->n, op->colind, v[0], v[1], v[0], v[0], c[0], c[1], 0, 0, x, beta, y); break;
-        case 3: spmv_multi_kernel<TPR, 3, VEC, ITERS><<<grid, 256, 0, st>>>(op->M, op->n, op->colind, v[0], v[1], v[2], v[0], c[0], c[1], c[2], 0, x, beta, y); break;
-        default: spmv_multi_kernel<TPR, 4, VEC, ITERS><<<grid, 256, 0, st>>>(op->M, op->n, op->colind, v[0], v[1], v[2], v[3], c[0], c[1], c[2], c[3], x, beta, y); break;
+        case 1: spmv_multi_kernel<TPR, 1, VEC, ITERS><<<grid, 256, 0, st>>>(op->M, op->n, op->colind, m, x, ep, y); break;
+        case 2: spmv_multi_kernel<TPR, 2, VEC, ITERS><<<grid, 256, 0, st>>>(op->M, op->n, op->colind, m, x, ep, y); break;
+        case 3: spmv_multi_kernel<TPR, 3, VEC, ITERS><<<grid, 256, 0, st>>>(op->M, op->n, op->colind, m, x, ep, y); break;
+        case 4: spmv_multi_kernel<TPR, 4, VEC, ITERS><<<grid, 256, 0, st>>>(op->M, op->n, op->colind, m, x, ep, y); break;
+        case 5: spmv_multi_kernel<TPR, 5, VEC, ITERS><<<grid, 256, 0, st>>>(op->M, op->n, op->colind, m, x, ep, y); break;
+        default: spmv_multi_kernel<TPR, 6, VEC, ITERS><<<grid, 256, 0, st>>>(op->M, op->n, op->colind, m, x, ep, y); break;
     }
     KLAUNCH(ctx);
     CUDA_TRY(ctx, cudaGetLastError());
@@ -112,33 +111,33 @@ int launch_multi(rbffd_operator* op, int nm, const double* const* v, const doubl
 }
 
 // row length -> (team size, vector width, unrolled iterations); TPR*VEC*ITERS >= n
-int dispatch_multi(rbffd_operator* op, int nm, const double* const* v, const double* c, const double* x, double beta, double* y) {
+int dispatch_multi(rbffd_operator* op, int nm, const SpmvMats& m, const double* x, const SpmvEpilogue& ep, double* y) {
     const int n = op->n;
     bool even = (n % 2) == 0;            // rows start 16-byte aligned when the planes are (n*8 bytes per row)
-    for (int i = 0; i < nm; ++i) even = even && (reinterpret_cast<uintptr_t>(v[i]) % 16 == 0);
+    for (int i = 0; i < nm; ++i) even = even && (reinterpret_cast<uintptr_t>(m.v[i]) % 16 == 0);
     even = even && (reinterpret_cast<uintptr_t>(op->colind) % 8 == 0);
     if (even) {
-        if (n <= 8) return launch_multi<4, 2, 1>(op, nm, v, c, x, beta, y);
-        if (n <= 16) return launch_multi<4, 2, 2>(op, nm, v, c, x, beta, y);
-        if (n <= 32) return launch_multi<8, 2, 2>(op, nm, v, c, x, beta, y);
-        if (n <= 48) return launch_multi<8, 2, 3>(op, nm, v, c, x, beta, y);
-        if (n <= 64) return launch_multi<8, 2, 4>(op, nm, v, c, x, beta, y);
-        if (n <= 128) return launch_multi<16, 2, 4>(op, nm, v, c, x, beta, y);
-        if (n <= 256) return launch_multi<32, 2, 4>(op, nm, v, c, x, beta, y);
+        if (n <= 8) return launch_multi<4, 2, 1>(op, nm, m, x, ep, y);
+        if (n <= 16) return launch_multi<4, 2, 2>(op, nm, m, x, ep, y);
+        if (n <= 32) return launch_multi<8, 2, 2>(op, nm, m, x, ep, y);
+        if (n <= 48) return launch_multi<8, 2, 3>(op, nm, m, x, ep, y);
+        if (n <= 64) return launch_multi<8, 2, 4>(op, nm, m, x, ep, y);
+        if (n <= 128) return launch_multi<16, 2, 4>(op, nm, m, x, ep, y);
+        if (n <= 256) return launch_multi<32, 2, 4>(op, nm, m, x, ep, y);
     } else {
-        if (n <= 8) return launch_multi<4, 1, 2>(op, nm, v, c, x, beta, y);
-        if (n <= 16) return launch_multi<4, 1, 4>(op, nm, v, c, x, beta, y);
-        if (n <= 32) return launch_multi<8, 1, 4>(op, nm, v, c, x, beta, y);
-        if (n <= 64) return launch_multi<8, 1, 8>(op, nm, v, c, x, beta, y);
-        if (n <= 128) return launch_multi<16, 1, 8>(op, nm, v, c, x, beta, y);
-        if (n <= 256) return launch_multi<32, 1, 8>(op, nm, v, c, x, beta, y);
+        if (n <= 8) return launch_multi<4, 1, 2>(op, nm, m, x, ep, y);
+        if (n <= 16) return launch_multi<4, 1, 4>(op, nm, m, x, ep, y);
+        if (n <= 32) return launch_multi<8, 1, 4>(op, nm, m, x, ep, y);
+        if (n <= 64) return launch_multi<8, 1, 8>(op, nm, m, x, ep, y);
+        if (n <= 128) return launch_multi<16, 1, 8>(op, nm, m, x, ep, y);
+        if (n <= 256) return launch_multi<32, 1, 8>(op, nm, m, x, ep, y);
     }
     RBFFD_FAIL(op->ctx, RBFFD_ERR_UNSUPPORTED, "spmv: row length %d > 256", n);
 }
 
 }  // namespace
 
-// y = sum_i coef[i] * D[which[i]] * x + beta * y ; terms are fused four at a time over the shared pattern
+// y = sum_i coef[i] * D[which[i]] * x + beta * y ; terms are fused six at a time over the shared pattern
 int rbffd_spmv_multi_impl(rbffd_operator* op, int nterms, const int32_t* which, const double* coef, const double* x,
                           double beta, double* y) {
     rbffd_context* ctx = op->ctx;
@@ -147,16 +146,31 @@ int rbffd_spmv_multi_impl(rbffd_operator* op, int nterms, const int32_t* which, 
         if (which[i] < 0 || which[i] >= op->nmat) RBFFD_FAIL(ctx, RBFFD_ERR_INVALID, "spmv: matrix index %d out of range (nmat=%d)", which[i], op->nmat);
     if (op->M == 0) return RBFFD_OK;
     const size_t stride = (size_t)op->M * op->n;
-    for (int i0 = 0; i0 < nterms; i0 += 4) {
-        const int nm = std::min(4, nterms - i0);
-        const double* v[4];
-        double c[4];
-        for (int i = 0; i < nm; ++i) { v[i] = op->vals + stride * which[i0 + i]; c[i] = coef[i0 + i]; }
-        const double b = i0 == 0 ? beta : 1.0;
-        int rc = dispatch_multi(op, nm, v, c, x, b, y);
-        RBFFD_TRY(rc);
+    for (int i0 = 0; i0 < nterms; i0 += SPMV_MAXMAT) {
+        const int nm = std::min(SPMV_MAXMAT, nterms - i0);
+        SpmvMats m{};
+        for (int i = 0; i < nm; ++i) { m.v[i] = op->vals + stride * which[i0 + i]; m.c[i] = coef[i0 + i]; }
+        const SpmvEpilogue ep{i0 == 0 ? beta : 1.0, nullptr, 0.0, 0.0, 0.0};
+        RBFFD_TRY(dispatch_multi(op, nm, m, x, ep, y));
     }
     return RBFFD_OK;
+}
+
+// out = a * u + b * (x + dt * sum_i coef[i] * D[which[i]] * x): one SSP-RK stage as ONE launch (rows = nodes, M == N, <= 6 terms)
+int rbffd_spmv_stage_impl(rbffd_operator* op, int nterms, const int32_t* which, const double* coef, const double* x,
+                          double a, const double* u, double b, double dt, double* out) {
+    rbffd_context* ctx = op->ctx;
+    if (nterms < 1 || nterms > SPMV_MAXMAT) RBFFD_FAIL(ctx, RBFFD_ERR_INVALID, "spmv_stage: 1..%d terms (combine the operators first)", SPMV_MAXMAT);
+    if (op->M != op->N) RBFFD_FAIL(ctx, RBFFD_ERR_INVALID, "spmv_stage: the stage update needs rows = nodes (M == N)");
+    if (out == x || out == u) RBFFD_FAIL(ctx, RBFFD_ERR_INVALID, "spmv_stage: out must not alias x or u (other rows still gather from them)");
+    for (int i = 0; i < nterms; ++i)
+        if (which[i] < 0 || which[i] >= op->nmat) RBFFD_FAIL(ctx, RBFFD_ERR_INVALID, "spmv_stage: matrix index %d out of range (nmat=%d)", which[i], op->nmat);
+    if (op->M == 0) return RBFFD_OK;
+    const size_t stride = (size_t)op->M * op->n;
+    SpmvMats m{};
+    for (int i = 0; i < nterms; ++i) { m.v[i] = op->vals + stride * which[i]; m.c[i] = coef[i]; }
+    const SpmvEpilogue ep{0.0, u, a, b, dt};
+    return dispatch_multi(op, nterms, m, x, ep, out);
 }
 
 int rbffd_build_transpose(rbffd_operator* op) {

@@ -4,6 +4,14 @@
 
 #include <cstdint>
 
+constexpr int SPMV_MAXMAT = 6;
+// up to six value planes over ONE shared pattern and their coefficients: y = sum_k c[k] * v[k] * x
+struct SpmvMats { const double* v[SPMV_MAXMAT]; double c[SPMV_MAXMAT]; };
+// what happens to the row sum `acc`:  su == nullptr:  y[row] = acc + beta * y[row]
+//                                     su != nullptr:  y[row] = sa * su[row] + sb * (x[row] + sdt * acc)   -- one SSP-RK stage
+//                                                     u_new = a u + b (v + dt L(v)) fused into the product (rows = nodes)
+struct SpmvEpilogue { double beta; const double* su; double sa, sb, sdt; };
+
 // TPR lanes cooperate on one row; a warp covers 32/TPR consecutive rows = one contiguous chunk of HBM.
 // Every lane first issues ALL of its value/index loads (streaming, evict-first), then the gathers of x
 // (read-only path, kept in L1/L2), then the FMAs: ITERS*VEC independent loads in flight per lane.
@@ -12,15 +20,19 @@
 // `warp` = index of this warp among the warps working on rows [row_begin, row_end).
 template <int TPR, int NMAT, int VEC, int ITERS, bool HALO>
 __device__ __forceinline__ void spmv_rows(int64_t warp, int64_t row_begin, int64_t row_end, int n, const int32_t* __restrict__ colind,
-                                          const double* __restrict__ v0, const double* __restrict__ v1,
-                                          const double* __restrict__ v2, const double* __restrict__ v3,
-                                          double c0, double c1, double c2, double c3,
-                                          const double* __restrict__ x, const double* __restrict__ xh, int n_owned,
-                                          double beta, double* __restrict__ y) {
+                                          const SpmvMats& m, const double* __restrict__ x, const double* __restrict__ xh, int n_owned,
+                                          const SpmvEpilogue& ep, double* __restrict__ y) {
     const int lane = threadIdx.x & 31;
     const int t = lane % TPR;
     const int64_t row = row_begin + warp * (32 / TPR) + lane / TPR;
     double acc = 0.0;
+    // the epilogue operands of the row are requested together with the matrix stream (lane 0 of the team), not after the
+    // reduction: a DRAM round trip at the end of every warp's life would halve the bytes in flight per SM
+    double e_u = 0.0, e_x = 0.0;
+    if (row < row_end && t == 0) {
+        if (ep.su) { e_u = __ldcs(ep.su + row); e_x = __ldg(x + row); }
+        else if (ep.beta != 0.0) e_u = __ldcs(y + row);
+    }
     if (row < row_end) {
         const int64_t base = row * n;
         int col[ITERS][VEC];
@@ -31,11 +43,13 @@ __device__ __forceinline__ void spmv_rows(int64_t warp, int64_t row_begin, int64
             if (VEC == 2) {
                 if (j < n) {
                     const int2 ci = __ldcs(reinterpret_cast<const int2*>(colind + base + j));
-                    double2 a0 = __ldcs(reinterpret_cast<const double2*>(v0 + base + j));
-                    a0.x *= c0; a0.y *= c0;
-                    if (NMAT > 1) { const double2 b = __ldcs(reinterpret_cast<const double2*>(v1 + base + j)); a0.x += c1 * b.x; a0.y += c1 * b.y; }
-                    if (NMAT > 2) { const double2 b = __ldcs(reinterpret_cast<const double2*>(v2 + base + j)); a0.x += c2 * b.x; a0.y += c2 * b.y; }
-                    if (NMAT > 3) { const double2 b = __ldcs(reinterpret_cast<const double2*>(v3 + base + j)); a0.x += c3 * b.x; a0.y += c3 * b.y; }
+                    double2 a0 = __ldcs(reinterpret_cast<const double2*>(m.v[0] + base + j));
+                    a0.x *= m.c[0]; a0.y *= m.c[0];
+#pragma unroll
+                    for (int k = 1; k < NMAT; ++k) {
+                        const double2 b = __ldcs(reinterpret_cast<const double2*>(m.v[k] + base + j));
+                        a0.x += m.c[k] * b.x; a0.y += m.c[k] * b.y;
+                    }
                     col[it][0] = ci.x; col[it][VEC - 1] = ci.y;
                     w[it][0] = a0.x; w[it][VEC - 1] = a0.y;
                 } else {
@@ -45,10 +59,9 @@ __device__ __forceinline__ void spmv_rows(int64_t warp, int64_t row_begin, int64
             } else {
                 if (j < n) {
                     col[it][0] = __ldcs(colind + base + j);
-                    double a0 = c0 * __ldcs(v0 + base + j);
-                    if (NMAT > 1) a0 += c1 * __ldcs(v1 + base + j);
-                    if (NMAT > 2) a0 += c2 * __ldcs(v2 + base + j);
-                    if (NMAT > 3) a0 += c3 * __ldcs(v3 + base + j);
+                    double a0 = m.c[0] * __ldcs(m.v[0] + base + j);
+#pragma unroll
+                    for (int k = 1; k < NMAT; ++k) a0 += m.c[k] * __ldcs(m.v[k] + base + j);
                     w[it][0] = a0;
                 } else {
                     col[it][0] = -1;
@@ -76,5 +89,8 @@ __device__ __forceinline__ void spmv_rows(int64_t warp, int64_t row_begin, int64
     }
 #pragma unroll
     for (int o = TPR / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if (row < row_end && t == 0) y[row] = beta == 0.0 ? acc : acc + beta * y[row];
+    if (row < row_end && t == 0) {
+        if (ep.su) y[row] = ep.sa * e_u + ep.sb * (e_x + ep.sdt * acc);
+        else y[row] = ep.beta == 0.0 ? acc : acc + ep.beta * e_u;
+    }
 }

@@ -151,6 +151,7 @@ int rbffd_validate_options(rbffd_context* ctx, const rbffd_options* o) {
     if (rc != RBFFD_OK) RBFFD_FAIL(ctx, rc, "%s", msg);
     if (o->index_base != 0 && o->index_base != 1) RBFFD_FAIL(ctx, RBFFD_ERR_INVALID, "index_base must be 0 or 1");
     if (o->variant != 0 && o->variant != 1) RBFFD_FAIL(ctx, RBFFD_ERR_INVALID, "variant must be 0 (two-set methods) or 1 (legacy collocated methods)");
+    if (o->index_width != 0 && o->index_width != 32 && o->index_width != 64) RBFFD_FAIL(ctx, RBFFD_ERR_INVALID, "index_width must be 0, 32 or 64");
     return RBFFD_OK;
 }
 

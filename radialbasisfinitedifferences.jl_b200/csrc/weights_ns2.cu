@@ -923,6 +923,153 @@ __global__ void __launch_bounds__(64, 8) ns2_elim_kernel(Ns2Args a) {
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// stage C, second form: ONE WARP per stencil and no barrier at all.  [S | t] stays in the warp's accumulator registers from
+// the load to the last pivot; the elimination runs by 4 x 4 block pivots (block_gj_warp, nullspace.cuh): the pivot block is
+// inverted redundantly in every lane and applied by DMMAs, so the scalar panel chain (4 pivots x search/scale/update per
+// block step), the panel and pivot-row dumps and the CTA barrier of every block step of ns2_elim_kernel are gone.  Warps of
+// a CTA are independent (each has its own slice of shared memory); occupancy is set by the registers (NT x NJ x 2 doubles).
+// ---------------------------------------------------------------------------------------------------------------------
+template <int D, int Q, int NT, int NJ>
+struct E1Cfg {
+    static constexpr int NBP = 8 * NT, WS = 8 * NJ + 4;
+    static constexpr int DSM = 32, WT = Q * WS, YS = 8 * NBP, HDR = NS2_REC_HDR / 8, PF = 8;
+    static constexpr int DOUBLES = DSM + WT + YS + HDR + PF;
+    static constexpr int BYTES = (DOUBLES * 8 + 64 * 4 + 15) & ~15;       // + perm[64]
+    static constexpr int WARPS = NT * NJ > 25 ? 3 : 4;                    // warps per CTA
+    static constexpr int MINB = NT * NJ > 25 ? 4 : 3;                     // CTAs per SM the register budget is set for
+};
+
+template <int D, int Q, int NT, int NJ>
+__global__ void __launch_bounds__(32 * E1Cfg<D, Q, NT, NJ>::WARPS, E1Cfg<D, Q, NT, NJ>::MINB) ns2_elim1_kernel(Ns2Args a) {
+    using C = E1Cfg<D, Q, NT, NJ>;
+    constexpr int NBP = C::NBP, WS = C::WS, NW = C::WARPS;
+    extern __shared__ __align__(16) unsigned char esm[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const OpTables& T = a.T;
+    const int n = T.n, nops = T.nops, nb = n - Q;
+    double* base = reinterpret_cast<double*>(esm + (size_t)warp * C::BYTES);
+    double* dsm = base;                               // [2][16] pivot blocks
+    double* Wt = dsm + C::DSM;                        // [Q][WS]
+    double* Ys = Wt + C::WT;                          // [8][NBP]
+    double* hdr = Ys + C::YS;                         // record header
+    double* pf = hdr + C::HDR;                        // [8]
+    int* perm = reinterpret_cast<int*>(pf + C::PF);   // [64]
+    const double sgn = (((T.p + 1) >> 1) & 1) ? -1.0 : 1.0;
+    const int sgnbits = sgn < 0.0 ? (int)0x80000000 : 0;
+    const int rcb = a.rcb;
+    for (int64_t i = (int64_t)blockIdx.x * NW + warp; i < a.cnt; i += (int64_t)gridDim.x * NW) {
+        const int64_t row = a.row0 + i;
+        const unsigned char* rec = a.rec + i * a.rec_stride;
+        // header and W'^T are needed only after the elimination: they stream in under it
+        if (lane < NS2_REC_HDR / 16) cp_async16(reinterpret_cast<unsigned char*>(hdr) + 16 * lane, rec + 16 * lane);
+        {
+            const double* Wg = reinterpret_cast<const double*>(rec + NS2_REC_W);
+            for (int idx = 2 * lane; idx < Q * WS; idx += 64) cp_async16(Wt + idx, Wg + idx);
+        }
+        cp_async_commit();
+        const double* Sg = a.stile + i * a.stile_stride;
+        double c[NT][NJ][2];
+#pragma unroll
+        for (int J = 0; J < NJ; ++J)
+#pragma unroll
+            for (int I = 0; I < NT; ++I) {
+                const double2 v = __ldcs(reinterpret_cast<const double2*>(Sg + (J * NT + I) * 64 + 2 * lane));
+                c[I][J][0] = v.x; c[I][J][1] = v.y;
+            }
+        const int bad = block_gj_warp<NT, NJ>(c, nb, dsm, sgnbits);
+        if (bad < 0) *a.redo = 1;
+        // the matrix is now [I | y]: y of operator o sits in column rcb + o
+#pragma unroll
+        for (int J = 0; J < NJ; ++J) {
+            if (8 * J + 8 > rcb && 8 * J < rcb + nops) {             // warp-uniform: tile columns that hold right-hand sides
+#pragma unroll
+                for (int I = 0; I < NT; ++I) {
+                    const int rw = 8 * I + g;
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const int o = 8 * J + 2 * t + e - rcb;
+                        if (rw < nb && o >= 0 && o < nops) Ys[o * NBP + rw] = c[I][J][e];
+                    }
+                }
+            }
+        }
+        cp_async_wait_all();
+        __syncwarp();
+        perm[lane] = reinterpret_cast<const unsigned char*>(hdr)[NS2_REC_PERM + lane];
+        perm[lane + 32] = reinterpret_cast<const unsigned char*>(hdr)[NS2_REC_PERM + lane + 32];
+        if (lane < nops) {
+            double s[D];
+#pragma unroll
+            for (int cdim = 0; cdim < D; ++cdim) s[cdim] = hdr[NS2_REC_S / 8 + cdim];
+            pf[lane] = op_post_factor<D>(T, lane, s);
+        }
+        __syncwarp();
+        // ---- w[N] = y, w[B] = w_p - W y; rescale and scatter into the CSR row (generate_operator.jl:161-182) ----
+        {
+            bool fin = true;
+            const double INF = __longlong_as_double(0x7ff0000000000000ll);
+            for (int P = lane; P < nb; P += 32) {
+                const int dst = perm[P];
+                for (int o = 0; o < nops; ++o) {
+                    const double wv = Ys[o * NBP + P] * pf[o];
+                    fin = fin && (fabs(wv) < INF);          // a zero pivot shows up as a non-finite weight
+                    a.vals[((int64_t)o * a.M + row) * n + dst] = wv;
+                }
+            }
+            for (int wt = 0; 8 * wt < Q; ++wt) {            // basic nodes: one DMMA row tile per trip (see ns2_solve_kernel)
+                const int cc = 8 * wt + g;
+                const bool rin = cc < Q;
+                const double* wrow = Wt + (rin ? cc : 0) * WS;
+                double c0 = (rin && 2 * t < nops) ? wrow[rcb + 2 * t] : 0.0;
+                double c1 = (rin && 2 * t + 1 < nops) ? wrow[rcb + 2 * t + 1] : 0.0;
+                const double* ycol = Ys + (g < nops ? g : 0) * NBP;
+#pragma unroll 2
+                for (int k0 = 0; k0 < nb; k0 += 4) {
+                    const int aa = k0 + t;
+                    const bool kin = aa < nb;
+                    const double af = (rin && kin) ? -wrow[kin ? aa : 0] : 0.0;
+                    const double bf = (g < nops && kin) ? ycol[kin ? aa : 0] : 0.0;
+                    dmma884(c0, c1, af, bf);
+                }
+                if (rin) {
+                    const int dst = perm[nb + cc];
+                    if (2 * t < nops) {
+                        const double wv = c0 * pf[2 * t];
+                        fin = fin && (fabs(wv) < INF);
+                        a.vals[((int64_t)(2 * t) * a.M + row) * n + dst] = wv;
+                    }
+                    if (2 * t + 1 < nops) {
+                        const double wv = c1 * pf[2 * t + 1];
+                        fin = fin && (fabs(wv) < INF);
+                        a.vals[((int64_t)(2 * t + 1) * a.M + row) * n + dst] = wv;
+                    }
+                }
+            }
+            if (!fin) *a.redo = 1;
+        }
+        __syncwarp();                                     // Wt, Ys, the header and perm are reused by the next stencil
+    }
+}
+
+template <int D, int Q, int NT, int NJ>
+int launch_elim1(rbffd_context* ctx, Ns2Args& a) {
+    using C = E1Cfg<D, Q, NT, NJ>;
+    const size_t smem = (size_t)C::BYTES * C::WARPS;
+    auto kern = ns2_elim1_kernel<D, Q, NT, NJ>;
+    CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 1;
+    CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32 * C::WARPS, smem));
+    per_sm = std::max(per_sm, 1);
+    static const int waves = [] { const char* e = getenv("RBFFD_NS2_ELIM_WAVES"); const int w = e ? atoi(e) : 0; return w > 0 ? w : 64; }();
+    const int grid = (int)std::min<int64_t>((a.cnt + C::WARPS - 1) / C::WARPS, (int64_t)ctx->sm_count * per_sm * waves);
+    kern<<<grid, 32 * C::WARPS, smem, ctx->stream>>>(a);
+    KLAUNCH(ctx);
+    CUDA_TRY(ctx, cudaGetLastError());
+    return RBFFD_OK;
+}
+
 template <int D, int Q, int NT, int NJ>
 int launch_elim(rbffd_context* ctx, Ns2Args& a) {
     constexpr int WS = 8 * NJ + 4, PS = 52, UST = 8 * NJ + 4;
@@ -967,7 +1114,9 @@ int launch_solve(rbffd_context* ctx, Ns2Args& a) {
     for (int k = 0; k < 6; ++k) fprintf(stderr, "[ns2 timing] %-26s %9.0f cycles/stencil\n", nm[k], (double)h[k] / (double)a.cnt);
 #endif
     if constexpr (NT <= 5) {
-        if (split) return launch_elim<D, Q, NT, NJ>(ctx, a);
+        // RBFFD_NS2_ELIM=2 keeps the two-warp elimination with its scalar panel chain (A/B comparisons)
+        static const int elim_env = [] { const char* e = getenv("RBFFD_NS2_ELIM"); return e ? atoi(e) : 1; }();
+        if (split) return elim_env == 2 ? launch_elim<D, Q, NT, NJ>(ctx, a) : launch_elim1<D, Q, NT, NJ>(ctx, a);
     }
     return RBFFD_OK;
 }

@@ -456,6 +456,11 @@ class Shard:
         w, c = self._terms(which, coef)
         self.ctx._check(self.ctx._L.rbffd_shard_spmv_device(self._h, op._h, len(which), w, c, x_ptr, y_ptr))
 
+    def spmv_stage_device(self, op, which, coef, x_ptr, a, u_ptr, b, dt, out_ptr):
+        """out[0:n_owned] = a*u + b*(x + dt * sum_i coef[i] D[which[i]] [x ; halo]): halo exchange + product + SSP-RK stage, ONE launch"""
+        w, c = self._terms(which, coef)
+        self.ctx._check(self.ctx._L.rbffd_shard_spmv_stage_device(self._h, op._h, len(which), w, c, x_ptr, a, u_ptr, b, dt, out_ptr))
+
     def spmv_local_device(self, op, which, coef, x_ptr, y_ptr):
         w, c = self._terms(which, coef)
         self.ctx._check(self.ctx._L.rbffd_shard_spmv_local_device(self._h, op._h, len(which), w, c, x_ptr, y_ptr))

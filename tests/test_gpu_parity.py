@@ -392,6 +392,76 @@ def test_spmv_and_rhs(ctx, oracle):
         op.spmv(0, u[:-1])
 
 
+def test_fused_cons_sys_and_stage_kernels(ctx, oracle):
+    """The collocated form of cons_sys (E = I checked on the device: all six operators in ONE pass over the shared pattern)
+    against the oracle's three-product form (adv_diff_test.jl:151-152): the two differ by the rounding noise of E's weights
+    (|E - I| <= eps * cond, here < 1e-9), the general path agrees to 1e-12; and the SSP-RK stage entry points
+    (rbffd_rhs_advdiff_stage_device, rbffd_spmv_stage_device, rbffd_stage_update_device) against NumPy on the same du."""
+    import torch
+    X = rb.nodes.jittered_lattice(2, 70, seed=6)
+    N = len(X)
+    names = ["E", "Dx", "Dy", "Dxx", "Dyy", ("Dk", 0, 4), ("Dk", 1, 4)]
+    colind, vals = rb.generate_raw(X, None, 5, 42, 5, names, ctx=ctx)
+    op = rb.Operator.from_host(ctx, colind, vals, N)
+    rng = np.random.default_rng(3)
+    x, u = rng.standard_normal(N), rng.standard_normal(N)
+    gamma = 100 * (1 / 70) ** 4
+    ref = oracle.rhs_advdiff(colind, *vals, 1.0, 0.5, -0.25, gamma, x)
+    scale = np.max(np.abs(ref))
+    general = rb.AdvDiffParams(iE=0, iDx=1, iDy=2, iDxx=3, iDyy=4, iDxk=5, iDyk=6, alpha=1.0, ux=0.5, uy=-0.25, gamma=gamma)
+    fused = rb.AdvDiffParams(iE=0, iDx=1, iDy=2, iDxx=3, iDyy=4, iDxk=5, iDyk=6, alpha=1.0, ux=0.5, uy=-0.25, gamma=gamma, flags=rb.ADVDIFF_COLLOCATED)
+    l0 = ctx.launch_count()
+    du_f = op.rhs_advdiff(x, fused)
+    first = ctx.launch_count() - l0                       # identity check (1 launch, once) + ONE product
+    l0 = ctx.launch_count()
+    du_f2 = op.rhs_advdiff(x, fused)
+    assert ctx.launch_count() - l0 == 1 and first == 2
+    assert np.array_equal(du_f, du_f2)
+    E_defect = np.abs(vals[0] - (colind == np.arange(N)[:, None])).max()
+    assert E_defect < 1e-9
+    assert np.max(np.abs(du_f - ref)) <= 4 * E_defect * scale
+    # ... and it IS the plain sum of the six products (no E anywhere)
+    six = sum(c * oracle.spmv(colind, vals[w], x) for w, c in zip([3, 4, 1, 2, 5, 6], [1.0, 1.0, -0.5, 0.25, -gamma, -gamma]))
+    assert np.max(np.abs(du_f - six)) <= 1e-12 * scale
+    du_g = op.rhs_advdiff(x, general)
+    assert np.max(np.abs(du_g - ref)) <= 1e-12 * scale
+    # an operator whose "E" is not the identity must keep the three-product form even when the flag is set
+    wrong = rb.AdvDiffParams(iE=1, iDx=1, iDy=2, iDxx=3, iDyy=4, iDxk=5, iDyk=6, alpha=1.0, ux=0.5, uy=-0.25, gamma=gamma, flags=rb.ADVDIFF_COLLOCATED)
+    vv = list(vals)
+    vv[0] = vals[1]
+    ref_w = oracle.rhs_advdiff(colind, *vv, 1.0, 0.5, -0.25, gamma, x)
+    op2 = rb.Operator.from_host(ctx, colind, vals, N)
+    assert np.max(np.abs(op2.rhs_advdiff(x, wrong) - ref_w)) <= 1e-12 * np.max(np.abs(ref_w))
+    # stage entry points
+    xd, ud = torch.from_numpy(x).cuda(), torch.from_numpy(u).cuda()
+    out = torch.empty_like(xd)
+    a, b, dt = 0.75, 0.25, 3e-4
+    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    op.rhs_advdiff_stage_device(xd.data_ptr(), a, ud.data_ptr(), b, dt, out.data_ptr(), fused)
+    torch.cuda.synchronize()
+    want = a * u + b * (x + dt * du_f)
+    assert np.max(np.abs(out.cpu().numpy() - want)) <= 4 * EPS * np.max(np.abs(want))
+    op.rhs_advdiff_stage_device(xd.data_ptr(), a, ud.data_ptr(), b, dt, out.data_ptr(), general)
+    torch.cuda.synchronize()
+    want = a * u + b * (x + dt * du_g)
+    assert np.max(np.abs(out.cpu().numpy() - want)) <= 4 * EPS * np.max(np.abs(want))
+    which, coef = [3, 4, 1, 2, 5, 6], [1.0, 1.0, -0.5, 0.25, -gamma, -gamma]
+    op.spmv_stage_device(which, coef, xd.data_ptr(), a, ud.data_ptr(), b, dt, out.data_ptr())
+    yd = torch.empty_like(xd)
+    op.spmv_multi_device(which, coef, xd.data_ptr(), yd.data_ptr())
+    torch.cuda.synchronize()
+    assert np.array_equal(yd.cpu().numpy(), du_f)         # six terms in one launch = the collocated cons_sys line
+    want = a * u + b * (x + dt * yd.cpu().numpy())
+    assert np.max(np.abs(out.cpu().numpy() - want)) <= 4 * EPS * np.max(np.abs(want))
+    dud = torch.from_numpy(du_f).cuda()
+    ctx.stage_update_device(N, a, ud.data_ptr(), b, xd.data_ptr(), dt, dud.data_ptr(), ud.data_ptr())       # in place on u
+    torch.cuda.synchronize()
+    assert np.max(np.abs(ud.cpu().numpy() - (a * u + b * (x + dt * du_f)))) <= 4 * EPS * np.max(np.abs(want))
+    with pytest.raises(rb.RbffdError):
+        op.spmv_stage_device(which, coef, xd.data_ptr(), a, ud.data_ptr(), b, dt, xd.data_ptr())            # out aliases x
+    ctx.reset_stream()
+
+
 def test_device_resident_pipeline_and_lattice(ctx, oracle):
     import torch
     dev = torch.device("cuda:0")
@@ -484,6 +554,8 @@ def test_device_resident_time_stepping_example(oracle, mesh):
         assert len(X) == 1812 and len(idx_in) == 1572                     # 1572 centroids + 120 BC + 120 ghosts
     else:
         X, u, (idx_in, idx_bc, idx_g) = mod.run(gy=gy, steps=steps, verbose=False)
+        Xg, ug, _ = mod.run(gy=gy, steps=steps, verbose=False, collocated=False)      # E' kept as a product (the reference's form)
+        assert np.max(np.abs(u - ug)) <= 1e-10 * np.max(np.abs(ug))
         h = 1.0 / gy
     N, n = len(X), 42
     groups = ((idx_in.start, idx_in.stop), [(r.start, r.stop) for r in idx_bc], [(r.start, r.stop) for r in idx_g])
@@ -665,14 +737,14 @@ def test_sharded_3d_time_stepping_example_one_gpu():
 
 
 def test_sharded_3d_time_stepping_example_two_gpus():
-    """The same run on two GPUs (slab shards, zero-communication generation, NVLink peer-memory halo exchange overlapped with
-    the interior rows) must reproduce the one-GPU result: identical stencils and weights, hence identical fields."""
+    """The same run on two GPUs (spatial-block shards, zero-communication generation, halo exchange fused into the SpMV launch,
+    CUDA-graph replay) must reproduce the one-GPU result: identical stencils and weights, hence identical fields."""
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     one = _run_example_3d(1, 30, 12)
-    two = _run_example_3d(2, 24, 12)          # G = round(24 * 2^(1/3)) = 30: the same global lattice
-    assert two["global_nodes"] == one["global_nodes"] and two["n_gpus"] == 2
+    two = _run_example_3d(2, 24, 12, ("--graph",))          # G = round(24 * 2^(1/3)) = 30: the same global lattice
+    assert two["global_nodes"] == one["global_nodes"] and two["n_gpus"] == 2 and two["cuda_graph"]
     assert abs(two["rel_l2_error_vs_exact"] - one["rel_l2_error_vs_exact"]) <= 1e-9 * one["rel_l2_error_vs_exact"]
     for a, b in zip(one["checksum"], two["checksum"]):
         assert abs(a - b) <= 1e-11 * abs(a)
