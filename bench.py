@@ -402,6 +402,26 @@ def main():
         total_nodes = int(c.item())
     ms_per_step = elapsed_ms / K
     value = total_nodes / (ms_per_step * 1e-3)
+    # ---- the operator application on its own: a loop of back-to-back products (the time-stepping regime).  Inside the step the
+    # product follows a 5 ms weight solve whose duration differs from rank to rank, so its in-step time at N > 1 contains that
+    # skew (the boundary rows wait for the slowest neighbour's values); the loop measures the product with its halo exchange.
+    y2 = torch.empty_like(y)
+    reps = 50
+    for _ in range(5):
+        (shard.spmv_device(op, [0], [1.0], u.data_ptr(), y2.data_ptr()) if world > 1 else op.spmv_device(0, u.data_ptr(), y2.data_ptr()))
+    barrier()
+    sp0, sp1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sp0.record(stream)
+    for _ in range(reps):
+        (shard.spmv_device(op, [0], [1.0], u.data_ptr(), y2.data_ptr()) if world > 1 else op.spmv_device(0, u.data_ptr(), y2.data_ptr()))
+    sp1.record(stream)
+    barrier()
+    spmv_loop_ms = sp0.elapsed_time(sp1) / reps
+    if world > 1:
+        t = torch.tensor([spmv_loop_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        spmv_loop_ms = float(t.item())
+    del y2
 
     if args.profile:
         if rank == 0:
@@ -473,6 +493,27 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
     e2e_value = total_nodes / e2e_s
+    # the same call with int32 indices in the caller's buffer (a SparseMatrixCSC{Float64,Int32}: no widening pass on the host)
+    opts32 = rb.make_options(dim, p, n, deg, CFG["ops"], kernel=args.kernel, index_width=32)
+    n_e2e = Xh.shape[0] if world == 1 else nc
+    ch32 = torch.empty((n_e2e, n), dtype=torch.int32).pin_memory()
+
+    def e2e32_step():
+        ctx._check(L.rbffd_generate_operator_host(ctx._h, byref(opts32), c_void_p(Xh.data_ptr()), n_e2e, None, n_e2e, None,
+                                                  c_void_p(ch32.data_ptr()), c_void_p(vh.data_ptr())))
+    e2e32_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(Ke):
+        e2e32_step()
+    e2e32_s = (time.perf_counter() - t0) / Ke
+    barrier()
+    if world > 1:
+        t = torch.tensor([e2e32_s], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e32_s = float(t.item())
+    same32 = bool(torch.equal(ch32.to(torch.int64), ch))
+    del ch32
     e2e_rows_ok = None
     if world > 1:
         # the owned rows of the host result, mapped to global ids, are the shard's rows (same stencil sets, same weights)
@@ -557,7 +598,8 @@ def main():
         F = flops_per_stencil(m, r)
         fp64_peak = max(peak["dfma_tflops"], peak["dmma_tflops"])
         ach_w = F * M / t_w * 1e-12
-        ach_s = spmv_bytes_per_row(n) * M / t_s * 1e-9
+        ach_s = spmv_bytes_per_row(n) * M / (spmv_loop_ms * 1e-3) * 1e-9
+        ach_s_step = spmv_bytes_per_row(n) * M / t_s * 1e-9
         traffic = {}
         try:
             traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("config%d" % args.config, {})
@@ -585,10 +627,15 @@ def main():
                                         "MEASURED_PEAKS.json has no FP64 entry" % (peak["dfma_tflops"], peak["dmma_tflops"])},
             "roofline_spmv": {"kernel": "spmv_multi_kernel" if world == 1 else "shard_spmv_kernel (halo exchange fused)", "bound": "hbm", "achieved": ach_s, "peak": hbm_peak, "unit": "GB/s",
                               "frac": ach_s / hbm_peak, "bytes_per_row": spmv_bytes_per_row(n), "traffic": traffic.get("spmv"),
-                              "peak_source": hbm_src, "note": "includes the halo exchange when N>1"},
+                              "ms": spmv_loop_ms, "achieved_in_step": ach_s_step, "frac_in_step": ach_s_step / hbm_peak,
+                              "peak_source": hbm_src,
+                              "note": "loop of %d back-to-back applications, max over ranks, halo exchange included when N>1 (per rank: %d rows); "
+                                      "the in-step figure also contains the rank-to-rank skew of the preceding weight solve" % (reps, M)},
             "knn": {"queries_per_s": M / t_k, "ms": t_k * 1e3},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": e2e_s * 1e3, "steps": Ke, "call": e2e_call, "owned_rows_verified": e2e_rows_ok},
+                    "ms_per_step": e2e_s * 1e3, "steps": Ke, "call": e2e_call, "owned_rows_verified": e2e_rows_ok,
+                    "int32_indices": {"value": total_nodes / e2e32_s, "ms_per_step": e2e32_s * 1e3, "d2h_bytes_per_step": d2h - (d2h // (8 + 8 * r)) * 4,
+                                      "same_pattern_as_int64": same32, "note": "opts.index_width = 32"}},
             "gpu_launches": int(launches),
             "clocks": clk,
         }

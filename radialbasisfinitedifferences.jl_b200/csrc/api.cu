@@ -357,16 +357,16 @@ int rbffd_generate_operator_host(rbffd_context* ctx, const rbffd_options* opts, 
         const unsigned lw = lw_env ? (unsigned)std::max(1, atoi(lw_env)) : 1u;
         // hardware threads THIS process may use: its affinity mask when the launcher bound it to the cores next to its GPU
         // (rb.bind_to_gpu_numa), else an equal share of the host
-        unsigned avail = hc / lw;
+        unsigned avail = hc / (2 * lw);
         {
             cpu_set_t set;
             CPU_ZERO(&set);
             if (sched_getaffinity(0, sizeof(set), &set) == 0) {
                 const unsigned bound = (unsigned)CPU_COUNT(&set);
-                if (bound > 0 && bound < hc) avail = bound;
+                if (bound > 0 && bound < hc) avail = bound > 1 ? bound - 1 : 1;      // bound process: all its threads but the caller's
             }
         }
-        const int T = wt_env ? std::max(1, atoi(wt_env)) : (int)std::max(1u, std::min(8u, avail / 2));
+        const int T = wt_env ? std::max(1, atoi(wt_env)) : (int)std::max(1u, std::min(8u, avail));
         // Several ranks on one host share its ingest bandwidth (measured at N = 2: 16.3 ms per call when every rank ships the
         // int64 pattern, 11.1 ms with the int32 pattern widened by 6 host threads per rank), so the int32 transfer is the
         // default at any rank count: the widening threads are capped by the cores of the rank, never replaced by an int64 copy.

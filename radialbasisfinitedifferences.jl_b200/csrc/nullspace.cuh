@@ -55,8 +55,9 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 //   * operands change fragment layout (accumulator -> A / B) by SHFL only.
 // Returns the OR of (sign bits of the 16 pivots of the LDL' factorisations) ^ sgnbits: negative when S is not definite.
 // dsm: 32 doubles of shared memory private to the warp.
-template <int NT, int NJ>
-__device__ __forceinline__ int block_gj_warp(double (&c)[NT][NJ][2], const int nb, double* __restrict__ dsm, const int sgnbits) {
+// (CI, CJ: declared extents of the accumulator array, >= NT, NJ)
+template <int NT, int NJ, int CI, int CJ>
+__device__ __forceinline__ int block_gj_warp(double (&c)[CI][CJ][2], const int nb, double* __restrict__ dsm, const int sgnbits) {
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
     int bad = 0;

@@ -26,6 +26,7 @@
 #include "common.cuh"
 #include "tables.cuh"
 #include "phs.cuh"
+#include "nullspace.cuh"
 
 namespace {
 
@@ -357,85 +358,20 @@ __global__ void __launch_bounds__(128, MINB) weights_ns_kernel(NArgs a) {
             asm volatile("prefetch.global.L1 [%0];" ::"l"(a.X + (int64_t)id_next * D));
             if (lane < D) asm volatile("prefetch.global.L1 [%0];" ::"l"(a.Y + (i + istride) * D + lane));
         }
-        constexpr int PS6 = 36, US6 = 36;                 // strides == 4 (mod 16): conflict-free fragment loads
-        double* Pbuf = G;                                 // [4][PS6]   (the Y tile is dead)
-        double* Lbuf = Pbuf + 4 * PS6;                    // [4][PS6]
-        double* Ubuf = Lbuf + 4 * PS6;                    // [4][US6]
-        double* rinv_s = Ubuf + 4 * US6;                  // [24]
-        double* const pb_w = Pbuf + (2 * (t & 1)) * PS6 + g;
-        const double* const lb_r = Lbuf + t * PS6 + g;
-        const double* const ub_r = Ubuf + t * US6 + g;
-#pragma unroll
-        for (int kb = 0; kb < 6; ++kb) {
-            if (4 * kb < nb) {                            // warp-uniform: identity-padded block steps are skipped
-                const int Jp = kb >> 1, h = kb & 1;
-                if ((t >> 1) == h) {
-#pragma unroll
-                    for (int I = 0; I < 3; ++I) {
-                        pb_w[8 * I] = c[I][Jp][0];
-                        pb_w[PS6 + 8 * I] = c[I][Jp][1];
-                    }
-                }
-                __syncwarp();
-                double av[4], w[4];
-#pragma unroll
-                for (int cc = 0; cc < 4; ++cc) { av[cc] = lane < NS_NB ? Pbuf[cc * PS6 + lane] : 0.0; w[cc] = 0.0; }
-#pragma unroll
-                for (int sidx = 0; sidx < 4; ++sidx) {
-                    const int pr = 4 * kb + sidx;         // static pivot row == lane pr
-                    double pv[4], wp[4];
-#pragma unroll
-                    for (int cc = sidx; cc < 4; ++cc) pv[cc] = __shfl_sync(FULL, av[cc], pr);
-#pragma unroll
-                    for (int cc = 0; cc < sidx; ++cc) wp[cc] = __shfl_sync(FULL, w[cc], pr);
-                    bad |= __double2hiint(pv[sidx]) ^ sgnbits;    // S not definite: the pivoted kernel must take over
-                    const double rinv = rcp3(pv[sidx]);
-                    if (lane == 0) rinv_s[pr] = rinv;
-                    const double nl = lane == pr ? 0.0 : av[sidx] * (-rinv);
-#pragma unroll
-                    for (int cc = sidx + 1; cc < 4; ++cc) av[cc] = fma(nl, pv[cc], av[cc]);
-#pragma unroll
-                    for (int cc = 0; cc < sidx; ++cc) w[cc] = fma(nl, wp[cc], w[cc]);
-                    w[sidx] = nl;
-                }
-                if (lane < NS_NB) {
-#pragma unroll
-                    for (int cc = 0; cc < 4; ++cc) Lbuf[cc * PS6 + lane] = w[cc];
-                }
-                // raw pivot rows 4kb .. 4kb+3: tile row kb>>1, lanes with g>>2 == kb&1
-                const int jlo = h == 0 ? Jp : Jp + 1;
-                if ((g >> 2) == h) {
-                    double2* dst = reinterpret_cast<double2*>(Ubuf + (g & 3) * US6 + 2 * t);
-#pragma unroll
-                    for (int J = 0; J < 4; ++J)
-                        if (J >= jlo && J < NJ) dst[4 * J] = make_double2(c[Jp][J][0], c[Jp][J][1]);
-                }
-                __syncwarp();
-                double af[3];
-#pragma unroll
-                for (int I = 0; I < 3; ++I) af[I] = lb_r[8 * I];
-#pragma unroll
-                for (int J = 0; J < 4; ++J) {
-                    if (J >= jlo && J < NJ) {
-                        const double bf = ub_r[8 * J];
-#pragma unroll
-                        for (int I = 0; I < 3; ++I) dmma884n(c[I][J][0], c[I][J][1], af[I], bf);
-                    }
-                }
-                __syncwarp();
-            }
-        }
-        // y = RHS_row / pivot_row  (right-hand-side column rcb + o lives in tile (rcb + o) / 8)
+        // 4 x 4 block pivots (nullspace.cuh): the pivot block is inverted in every lane and applied by DMMAs, operands change
+        // fragment layout by SHFL -- no panel / pivot-row dumps through shared memory, one __syncwarp per block step
+        __syncwarp();                                     // every lane is done with the Y tile: its first 256 B carry the pivot blocks
+        bad |= nsp::block_gj_warp<3, NJ, 4, 4>(c, nb, G, sgnbits);
+        // the matrix is now [I | y]  (right-hand-side column rcb + o lives in tile (rcb + o) / 8)
 #pragma unroll
         for (int I = 0; I < 3; ++I) {
             const int row = 8 * I + g;
-            const double ri = rinv_s[row < nb ? row : 0];
 #pragma unroll
             for (int J = 0; J < 4; ++J)
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
                     const int o = 8 * J + 2 * t + e - rcb;
-                    if (row < nb && J < NJ && o >= 0 && o < nops) Ys[o * NS_NB + row] = c[I][J][e] * ri;
+                    if (row < nb && J < NJ && o >= 0 && o < nops) Ys[o * NS_NB + row] = c[I][J][e];
                 }
         }
         __syncwarp();

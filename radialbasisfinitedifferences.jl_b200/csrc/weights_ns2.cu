@@ -44,6 +44,12 @@ struct Ns2Args {
     int32_t ws, rcb;           // row stride of the transposed W' block, position of the first w_p row
     double* stile;             // split path: [S | t] of every stencil of the chunk as DMMA accumulator tiles,
     int64_t stile_stride;      //   tile (I, J) of record k at stile + k * stile_stride + (J * NT + I) * 64, lane l holds doubles 2l, 2l+1
+    // pure even-order axis derivatives d^K/dx_a^K r^p (the hyperviscosity operators of rbfbasis_k.jl:9-18): the term list
+    // sum_j c_j x^(K-2j) r^(p-2K+2j) is r^(p-K) times a polynomial of degree K/2 in u = (x/r)^2, evaluated by Horner
+    int8_t hv_axis[8];         // -1: not of this form
+    int8_t hv_half[8];         // K / 2
+    int8_t hv_rexp[8];         // p - K (odd, >= 1)
+    double hv_c[8][4];         // coefficient of u^k
     OpTables T;
 };
 
@@ -446,9 +452,22 @@ __global__ void __launch_bounds__(128, 4) ns2_solve_kernel(Ns2Args a) {
                 int order = 0;
 #pragma unroll
                 for (int c = 0; c < D; ++c) order += T.alpha[o][c];
-                Bt[P * BS + o] = (T.kind[o] == RBFFD_OP_DERIV && order > 2)
-                                     ? eval_rbf_terms_rinv<D>(T, T.tb[3 * o], T.tb[3 * o + 1], del, r, r2, y)     // hyperviscosity closed forms
-                                     : rhs_rbf_entry_fast<D>(T, o, del, s, r, r2, rp, rp2, rp4);
+                double val;
+                if (a.hv_axis[o] >= 0) {                    // hyperviscosity closed form: r^(p-K) * poly((x/r)^2)
+                    const int ax = a.hv_axis[o], half = a.hv_half[o];
+                    const double xa = ax == 0 ? del[0] : (ax == 1 ? del[1] : del[D - 1]);
+                    const double xi = xa * y, u = xi * xi;
+                    double pv = a.hv_c[o][half];
+                    for (int kk = half - 1; kk >= 0; --kk) pv = fma(pv, u, a.hv_c[o][kk]);
+                    double rr = r;
+                    for (int e = 1; e < a.hv_rexp[o]; e += 2) rr *= r2;
+                    val = rr * pv;
+                } else if (T.kind[o] == RBFFD_OP_DERIV && order > 2) {
+                    val = eval_rbf_terms_rinv<D>(T, T.tb[3 * o], T.tb[3 * o + 1], del, r, r2, y);                  // other closed forms: term lists
+                } else {
+                    val = rhs_rbf_entry_fast<D>(T, o, del, s, r, r2, rp, rp2, rp4);
+                }
+                Bt[P * BS + o] = val;
             }
         }
         __syncthreads();                              // Sc complete; header and Xn are consumed
@@ -978,7 +997,7 @@ __global__ void __launch_bounds__(32 * E1Cfg<D, Q, NT, NJ>::WARPS, E1Cfg<D, Q, N
                 const double2 v = __ldcs(reinterpret_cast<const double2*>(Sg + (J * NT + I) * 64 + 2 * lane));
                 c[I][J][0] = v.x; c[I][J][1] = v.y;
             }
-        const int bad = block_gj_warp<NT, NJ>(c, nb, dsm, sgnbits);
+        const int bad = block_gj_warp<NT, NJ, NT, NJ>(c, nb, dsm, sgnbits);
         if (bad < 0) *a.redo = 1;
         // the matrix is now [I | y]: y of operator o sits in column rcb + o
 #pragma unroll
@@ -1205,6 +1224,25 @@ int rbffd_weights_ns2(rbffd_context* ctx, const OpTables& T, const double* X, in
             }
             if (hit) { a.gzcol[o] = c; a.gzval[o] = v; }
         }
+    }
+    for (int o = 0; o < 8; ++o) {
+        a.hv_axis[o] = -1; a.hv_half[o] = 0; a.hv_rexp[o] = 1;
+        for (int k = 0; k < 4; ++k) a.hv_c[o][k] = 0.0;
+        if (o >= T.nops || T.kind[o] != RBFFD_OP_DERIV) continue;
+        int ax = -1, K = 0, nz = 0;
+        for (int b = 0; b < T.dim; ++b) if (T.alpha[o][b] > 0) { ax = b; K = T.alpha[o][b]; ++nz; }
+        if (nz != 1 || K < 4 || (K & 1) || K > 6 || K >= T.p) continue;
+        bool ok = true;
+        double cf[4] = {0, 0, 0, 0};
+        for (int t = T.tb[3 * o]; t < T.tb[3 * o + 1] && ok; ++t) {
+            const int ea = T.te[t][ax];
+            for (int b = 0; b < T.dim; ++b) if (b != ax && T.te[t][b] != 0) ok = false;
+            if (ea < 0 || ea > K || (ea & 1) || T.te[t][3] != T.p - K - ea) ok = false;     // x^ea r^(p-K-ea) = r^(p-K) (x/r)^ea
+            if (ok) cf[ea / 2] += T.coef[t];
+        }
+        if (!ok) continue;
+        a.hv_axis[o] = (int8_t)ax; a.hv_half[o] = (int8_t)(K / 2); a.hv_rexp[o] = (int8_t)(T.p - K);
+        for (int k = 0; k < 4; ++k) a.hv_c[o][k] = cf[k];
     }
     DevBuf<int> redo;
     const bool deferred = ctx->deferred_flags != nullptr;
