@@ -134,6 +134,16 @@ int rbffd_stencils_device(rbffd_context* ctx, const double* X, int64_t N, int32_
 int rbffd_operator_generate(rbffd_context* ctx, const rbffd_options* opts,
                             const double* X_dev, int64_t N, const double* Y_dev, int64_t M,
                             const int32_t* xgroup_dev, rbffd_operator** op);
+/* the same from HOST coordinates (a host language without its own device arrays, e.g. Julia without CUDA.jl): uploads X / Y /
+ * the group codes, generates on the device and returns the handle; nothing of size nnz crosses PCIe */
+int rbffd_operator_generate_host(rbffd_context* ctx, const rbffd_options* opts, const double* X, int64_t N, const double* Y, int64_t M,
+                                 const int32_t* xgroup, rbffd_operator** op);
+/* plain device buffers for such callers (field vectors of the time loop): cudaMalloc / cudaFree / synchronous copies on the
+ * context's stream */
+int rbffd_device_malloc(rbffd_context* ctx, int64_t bytes, void** ptr);
+int rbffd_device_free(rbffd_context* ctx, void* ptr);
+int rbffd_device_upload(rbffd_context* ctx, void* dst_device, const void* src_host, int64_t bytes);
+int rbffd_device_download(rbffd_context* ctx, void* dst_host, const void* src_device, int64_t bytes);
 /* wrap host CSR data (fixed row length) */
 int rbffd_operator_from_host(rbffd_context* ctx, int64_t M, int64_t N, int32_t n, int32_t nmat,
                              const int64_t* colind, int32_t index_base, const double* vals, rbffd_operator** op);

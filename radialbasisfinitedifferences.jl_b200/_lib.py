@@ -75,6 +75,11 @@ _SIGNATURES = {
     "rbffd_launch_count": ([_vp], C.c_longlong),
     "rbffd_measure_fp64_peak": ([_vp, C.POINTER(_dbl), C.POINTER(_dbl)], C.c_int),
     "rbffd_operator_generate": ([_vp, C.POINTER(Options), _vp, _i64, _vp, _i64, _vp, C.POINTER(_vp)], C.c_int),
+    "rbffd_operator_generate_host": ([_vp, C.POINTER(Options), _vp, _i64, _vp, _i64, _vp, C.POINTER(_vp)], C.c_int),
+    "rbffd_device_malloc": ([_vp, _i64, C.POINTER(_vp)], C.c_int),
+    "rbffd_device_free": ([_vp, _vp], C.c_int),
+    "rbffd_device_upload": ([_vp, _vp, _vp, _i64], C.c_int),
+    "rbffd_device_download": ([_vp, _vp, _vp, _i64], C.c_int),
     "rbffd_operator_from_host": ([_vp, _i64, _i64, _i32, _i32, _vp, _i32, _vp, C.POINTER(_vp)], C.c_int),
     "rbffd_operator_from_device": ([_vp, _i64, _i64, _i32, _i32, _vp, _vp, C.POINTER(_vp)], C.c_int),
     "rbffd_stencils_device": ([_vp, _vp, _i64, _i32, _vp, _i64, _i32, _vp, _vp, _vp], C.c_int),

@@ -565,6 +565,69 @@ int rbffd_operator_generate(rbffd_context* ctx, const rbffd_options* opts, const
     return RBFFD_OK;
 }
 
+int rbffd_operator_generate_host(rbffd_context* ctx, const rbffd_options* opts, const double* X, int64_t N, const double* Y, int64_t M,
+                                 const int32_t* xgroup, rbffd_operator** out) {
+    if (!ctx) return RBFFD_ERR_INVALID;
+    if (!out) RBFFD_FAIL(ctx, RBFFD_ERR_INVALID, "operator_generate_host: NULL output handle");
+    *out = nullptr;
+    RBFFD_TRY(rbffd_validate_options(ctx, opts));
+    if (!X || N < 1) RBFFD_FAIL(ctx, RBFFD_ERR_INVALID, "operator_generate_host: X is empty");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const int dim = opts->dim;
+    DevBuf<double> dX, dY;
+    DevBuf<int32_t> dG;
+    CUDA_TRY(ctx, dX.alloc((size_t)N * dim, st));
+    CUDA_TRY(ctx, cudaMemcpyAsync(dX.p, X, sizeof(double) * N * dim, cudaMemcpyHostToDevice, st));
+    if (Y && Y != X) {
+        if (M < 1) RBFFD_FAIL(ctx, RBFFD_ERR_INVALID, "operator_generate_host: Y is empty");
+        CUDA_TRY(ctx, dY.alloc((size_t)M * dim, st));
+        CUDA_TRY(ctx, cudaMemcpyAsync(dY.p, Y, sizeof(double) * M * dim, cudaMemcpyHostToDevice, st));
+    }
+    if (xgroup) {
+        CUDA_TRY(ctx, dG.alloc(N, st));
+        CUDA_TRY(ctx, cudaMemcpyAsync(dG.p, xgroup, sizeof(int32_t) * N, cudaMemcpyHostToDevice, st));
+    }
+    const bool two = Y && Y != X;
+    int rc = rbffd_operator_generate(ctx, opts, dX.p, N, two ? dY.p : nullptr, two ? M : N, xgroup ? dG.p : nullptr, out);
+    cudaStreamSynchronize(st);
+    return rc;
+}
+
+int rbffd_device_malloc(rbffd_context* ctx, int64_t bytes, void** ptr) {
+    if (!ctx) return RBFFD_ERR_INVALID;
+    if (!ptr || bytes < 0) RBFFD_FAIL(ctx, RBFFD_ERR_INVALID, "device_malloc: bad arguments");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    CUDA_TRY(ctx, cudaMalloc(ptr, (size_t)std::max<int64_t>(bytes, 1)));
+    return RBFFD_OK;
+}
+
+int rbffd_device_free(rbffd_context* ctx, void* ptr) {
+    if (!ctx) return RBFFD_ERR_INVALID;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ptr) CUDA_TRY(ctx, cudaFree(ptr));
+    return RBFFD_OK;
+}
+
+int rbffd_device_upload(rbffd_context* ctx, void* dst, const void* src, int64_t bytes) {
+    if (!ctx) return RBFFD_ERR_INVALID;
+    if (bytes < 0 || (bytes > 0 && (!dst || !src))) RBFFD_FAIL(ctx, RBFFD_ERR_INVALID, "device_upload: bad arguments");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    if (bytes > 0) CUDA_TRY(ctx, cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return RBFFD_OK;
+}
+
+int rbffd_device_download(rbffd_context* ctx, void* dst, const void* src, int64_t bytes) {
+    if (!ctx) return RBFFD_ERR_INVALID;
+    if (bytes < 0 || (bytes > 0 && (!dst || !src))) RBFFD_FAIL(ctx, RBFFD_ERR_INVALID, "device_download: bad arguments");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    if (bytes > 0) CUDA_TRY(ctx, cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return RBFFD_OK;
+}
+
 int rbffd_operator_from_host(rbffd_context* ctx, int64_t M, int64_t N, int32_t n, int32_t nmat, const int64_t* colind,
                              int32_t index_base, const double* vals, rbffd_operator** out) {
     if (!ctx) return RBFFD_ERR_INVALID;

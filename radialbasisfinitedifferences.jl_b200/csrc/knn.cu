@@ -110,29 +110,6 @@ __device__ __forceinline__ bool lessp(double da, int ia, double db, int ib) {
     return da < db || (da == db && ia < ib);
 }
 
-// put (vd, vi) into the hole at i0 of a max-heap of size n and sift it down
-__device__ __forceinline__ void sift_down(double* hd, int* hi, int S, int n, int i0, double vd, int vi) {
-    int i = i0;
-    for (;;) {
-        int l = 2 * i + 1;
-        if (l >= n) break;
-        int c = l;
-        double cd = hd[l * S];
-        int ci = hi[l * S];
-        if (l + 1 < n) {
-            double rd = hd[(l + 1) * S];
-            int ri = hi[(l + 1) * S];
-            if (lessp(cd, ci, rd, ri)) { c = l + 1; cd = rd; ci = ri; }
-        }
-        if (!lessp(vd, vi, cd, ci)) break;
-        hd[i * S] = cd;
-        hi[i * S] = ci;
-        i = c;
-    }
-    hd[i * S] = vd;
-    hi[i * S] = vi;
-}
-
 struct KnnArgs {
     Grid g;
     const double* xs;          // SoA sorted coordinates [D][N]
@@ -150,14 +127,21 @@ struct KnnArgs {
 
 constexpr int KNN_BS = 128;
 
+// One thread per query.  The k-candidate max-heap of a thread is a column of shared memory holding, per entry, the squared
+// distance ROUNDED TO FLOAT and the candidate's slot in the cell-sorted arrays: 8 bytes instead of the 12 of (double, caller
+// index), i.e. 1.5x - 2x the resident warps of this latency-bound kernel (at k = 60 the heap alone is 62 KB per 128 queries).
+// Rounding to float is monotone, so float keys that differ order the candidates exactly as the doubles do; only when two float
+// keys are EQUAL are the two squared distances recomputed in double from the coordinates (same ((dx*dx)+dy*dy)+dz*dz arithmetic)
+// and, on an exact tie, the caller indices compared -- results are bit-identical to a heap of doubles, exact-tie lattices
+// included (they just take the slow comparison more often).
 template <int D>
 __global__ void __launch_bounds__(KNN_BS) knn_kernel(KnnArgs a) {
     extern __shared__ unsigned char knn_smem[];
     const int tid = threadIdx.x;
     const int S = KNN_BS + 1;
     const int k = a.k;
-    double* hd = reinterpret_cast<double*>(knn_smem) + tid;
-    int* hi = reinterpret_cast<int*>(knn_smem + sizeof(double) * (size_t)S * k) + tid;
+    float* hf = reinterpret_cast<float*>(knn_smem) + tid;
+    int* hs = reinterpret_cast<int*>(knn_smem + sizeof(float) * (size_t)S * k) + tid;
     const int64_t t = blockIdx.x * (int64_t)KNN_BS + tid;
     if (t >= a.NQ) return;
     const Grid& g = a.g;
@@ -184,9 +168,59 @@ __global__ void __launch_bounds__(KNN_BS) knn_kernel(KnnArgs a) {
         slack = fmax(slack, 1e-9 * g.h[c]);
     }
 
+    auto exact_d2 = [&](int i) -> double {
+        double dx = __dsub_rn(q[0], a.xs[i]);
+        double d2 = __dmul_rn(dx, dx);
+        if (D > 1) {
+            double dy = __dsub_rn(q[1], a.xs[a.N + i]);
+            d2 = __dadd_rn(d2, __dmul_rn(dy, dy));
+        }
+        if (D > 2) {
+            double dz = __dsub_rn(q[D - 1], a.xs[2 * a.N + i]);
+            d2 = __dadd_rn(d2, __dmul_rn(dz, dz));
+        }
+        return d2;
+    };
+    // (d2, caller index) order on (float key, slot) pairs
+    auto less_fs = [&](float fa, int sa, float fb, int sb) -> bool {
+        if (fa != fb) return fa < fb;
+        const double da = exact_d2(sa), db = exact_d2(sb);
+        if (da != db) return da < db;
+        return a.perm[sa] < a.perm[sb];
+    };
+    // put (vf, vs) into the hole at i0 of a max-heap of size n and sift it down
+    auto sift_down = [&](int n, int i0, float vf, int vs) {
+        int i = i0;
+        for (;;) {
+            int l = 2 * i + 1;
+            if (l >= n) break;
+            int c = l;
+            float cf = hf[l * S];
+            int cs = hs[l * S];
+            if (l + 1 < n) {
+                const float rf = hf[(l + 1) * S];
+                const int rs = hs[(l + 1) * S];
+                if (less_fs(cf, cs, rf, rs)) { c = l + 1; cf = rf; cs = rs; }
+            }
+            if (!less_fs(vf, vs, cf, cs)) break;
+            hf[i * S] = cf;
+            hs[i * S] = cs;
+            i = c;
+        }
+        hf[i * S] = vf;
+        hs[i * S] = vs;
+    };
+
     int cnt = 0;
-    double wd = DBL_MAX;
-    int wi = 0x7fffffff;
+    float wf = FLT_MAX;            // float key of the current k-th candidate (heap root) once cnt == k
+    int ws = 0;
+    double wd_ub = DBL_MAX;        // an upper bound of its exact squared distance: the next float above wf
+
+    auto set_root = [&]() {
+        wf = hf[0];
+        ws = hs[0];
+        wd_ub = wf < FLT_MAX ? (double)__int_as_float(__float_as_int(wf) + 1) : DBL_MAX;
+    };
 
     auto scan_run = [&](int y, int z, int x0, int x1) {
         if (cnt == k) {
@@ -206,43 +240,33 @@ __global__ void __launch_bounds__(KNN_BS) knn_kernel(KnnArgs a) {
                 double gp = fmax(loz - q[D - 1], q[D - 1] - hiz) - slack;
                 if (gp > 0.0) m2 += gp * gp;
             }
-            if (m2 > wd) return;
+            if (m2 > wd_ub) return;
         }
         const int base = (D == 3 ? (z * g.n[1] + y) : (D == 2 ? y : 0)) * g.n[0];
         const int s = a.cell_start[base + x0], e = a.cell_start[base + x1 + 1];
         for (int i = s; i < e; ++i) {
-            double dx = __dsub_rn(q[0], a.xs[i]);
-            double d2 = __dmul_rn(dx, dx);
-            if (D > 1) {
-                double dy = __dsub_rn(q[1], a.xs[a.N + i]);
-                d2 = __dadd_rn(d2, __dmul_rn(dy, dy));
-            }
-            if (D > 2) {
-                double dz = __dsub_rn(q[D - 1], a.xs[2 * a.N + i]);
-                d2 = __dadd_rn(d2, __dmul_rn(dz, dz));
-            }
-            if (cnt == k && d2 > wd) continue;
+            const double d2 = exact_d2(i);
+            const float f = __double2float_rn(d2);
+            if (cnt == k && f > wf) continue;                  // a larger float key is a larger squared distance
             if (a.sgroup && !visible(qg, a.sgroup[i])) continue;
-            const int id = a.perm[i];
             if (cnt < k) {
                 // sift up
                 int j = cnt;
                 while (j > 0) {
                     int p = (j - 1) >> 1;
-                    double pd = hd[p * S];
-                    int pi = hi[p * S];
-                    if (!lessp(pd, pi, d2, id)) break;
-                    hd[j * S] = pd;
-                    hi[j * S] = pi;
+                    const float pf = hf[p * S];
+                    const int ps = hs[p * S];
+                    if (!less_fs(pf, ps, f, i)) break;
+                    hf[j * S] = pf;
+                    hs[j * S] = ps;
                     j = p;
                 }
-                hd[j * S] = d2;
-                hi[j * S] = id;
-                if (++cnt == k) { wd = hd[0]; wi = hi[0]; }
-            } else if (lessp(d2, id, wd, wi)) {
-                sift_down(hd, hi, S, k, 0, d2, id);
-                wd = hd[0];
-                wi = hi[0];
+                hf[j * S] = f;
+                hs[j * S] = i;
+                if (++cnt == k) set_root();
+            } else if (less_fs(f, i, wf, ws)) {
+                sift_down(k, 0, f, i);
+                set_root();
             }
         }
     };
@@ -265,7 +289,9 @@ __global__ void __launch_bounds__(KNN_BS) knn_kernel(KnnArgs a) {
             }
             if (!any) break;                       // grid exhausted
             lb -= slack;
-            if (cnt == k && lb > 0.0 && lb * lb > wd) break;
+            // exact test against the k-th candidate (its distance recomputed in double; the float bound first)
+            if (cnt == k && lb > 0.0 && lb * lb > wd_ub) break;
+            if (cnt == k && lb > 0.0 && lb * lb > exact_d2(ws)) break;
         }
         const int x0 = max(cc[0] - R, 0), x1 = min(cc[0] + R, g.n[0] - 1);
         if (D == 1) {
@@ -306,18 +332,18 @@ __global__ void __launch_bounds__(KNN_BS) knn_kernel(KnnArgs a) {
 
     // heap sort -> ascending by (d2, idx)
     for (int e = cnt - 1; e > 0; --e) {
-        double td = hd[e * S];
-        int ti = hi[e * S];
-        hd[e * S] = hd[0];
-        hi[e * S] = hi[0];
-        sift_down(hd, hi, S, e, 0, td, ti);
+        const float tf = hf[e * S];
+        const int ts = hs[e * S];
+        hf[e * S] = hf[0];
+        hs[e * S] = hs[0];
+        sift_down(e, 0, tf, ts);
     }
     if (cnt < k) atomicAdd(a.short_rows, 1);
     int32_t* orow = a.idx_out + row * k;
-    for (int j = 0; j < k; ++j) orow[j] = j < cnt ? hi[j * S] : -1;
+    for (int j = 0; j < k; ++j) orow[j] = j < cnt ? a.perm[hs[j * S]] : -1;
     if (a.d2_out) {
         double* drow = a.d2_out + row * k;
-        for (int j = 0; j < k; ++j) drow[j] = j < cnt ? hd[j * S] : INFINITY;
+        for (int j = 0; j < k; ++j) drow[j] = j < cnt ? exact_d2(hs[j * S]) : INFINITY;
     }
 }
 
@@ -441,7 +467,7 @@ int run_knn(rbffd_context* ctx, const Bins& B, const double* Q, int64_t NQ, cons
     CUDA_TRY(ctx, flag.alloc(1, st));
     CUDA_TRY(ctx, cudaMemsetAsync(flag.p, 0, sizeof(int), st));
     a.short_rows = flag.p;
-    size_t smem = (size_t)(KNN_BS + 1) * k * (sizeof(double) + sizeof(int));
+    size_t smem = (size_t)(KNN_BS + 1) * k * (sizeof(float) + sizeof(int));
     if ((int64_t)smem > ctx->max_smem_optin)
         RBFFD_FAIL(ctx, RBFFD_ERR_UNSUPPORTED, "k=%d needs %zu B of shared memory per block (max %d)", k, smem, ctx->max_smem_optin);
     const int nb = ceil_div_i64(NQ, KNN_BS);

@@ -768,3 +768,51 @@ def test_legacy_collocated_methods(ctx, oracle):
         rb.generate_raw(X, X + 1e-3, 3, 20, 3, ["E"], ctx=ctx, variant=1)        # the legacy methods take X only
     with pytest.raises(rb.RbffdError):
         rb.generate_raw(X, None, 3, 20, 3, ["E"], ctx=ctx, variant=1, kernel=3)
+
+
+def test_host_language_device_path(ctx, oracle):
+    """What julia/RBFFDB200.jl does for the device-resident time loop, call for call through ctypes: operators generated from
+    HOST node sets straight into HBM (rbffd_operator_generate_host), field vectors in library buffers (rbffd_device_*), one
+    cons_sys + stage combination on them; and the int32 host index option (SparseMatrixCSC{Float64,Int32})."""
+    import ctypes as C
+    X = rb.nodes.jittered_lattice(2, 50, seed=8)
+    N, n = len(X), 42
+    names = ["E", "Dx", "Dy", "Dxx", "Dyy", ("Dk", 0, 4), ("Dk", 1, 4)]
+    opts = rb.make_options(2, 5, n, 5, names)
+    L = ctx._L
+    h = C.c_void_p()
+    ctx._check(L.rbffd_operator_generate_host(ctx._h, C.byref(opts), X.ctypes.data, N, None, N, None, C.byref(h)))
+    op = rb.Operator(ctx, h)
+    colind, vals = rb.generate_raw(X, None, 5, n, 5, names, ctx=ctx)
+    lc, lv = op.to_host()
+    assert np.array_equal(lc, colind) and np.array_equal(lv, vals)
+    u = np.random.default_rng(4).standard_normal(N)
+    bufs = []
+    for _ in range(3):
+        p = C.c_void_p()
+        ctx._check(L.rbffd_device_malloc(ctx._h, 8 * N, C.byref(p)))
+        bufs.append(p)
+    du_d, u_d, out_d = bufs
+    ctx._check(L.rbffd_device_upload(ctx._h, u_d, u.ctypes.data, 8 * N))
+    gamma = 100 * (1 / 50) ** 4
+    prm = rb.AdvDiffParams(iE=0, iDx=1, iDy=2, iDxx=3, iDyy=4, iDxk=5, iDyk=6, alpha=1.0, ux=0.3, uy=-0.2, gamma=gamma)
+    op.rhs_advdiff_device(u_d, du_d, prm)
+    ctx.stage_update_device(N, 0.75, u_d, 0.25, u_d, 1e-4, du_d, out_d)
+    got = np.empty(N)
+    ctx._check(L.rbffd_device_download(ctx._h, got.ctypes.data, out_d, 8 * N))
+    du = oracle.rhs_advdiff(colind, *vals, 1.0, 0.3, -0.2, gamma, u)
+    want = 0.75 * u + 0.25 * (u + 1e-4 * du)
+    assert np.max(np.abs(got - want)) <= 1e-12 * np.max(np.abs(want))
+    for p in bufs:
+        ctx._check(L.rbffd_device_free(ctx._h, p))
+    op.close()
+    # int32 indices straight into the caller's buffer, one-shot and pipelined (pinned) paths, 1-based as Julia asks
+    c32, v32 = rb.generate_raw(X, None, 5, n, 5, names[:3], ctx=ctx, index_base=1, index_width=32)
+    assert c32.dtype == np.int32 and np.array_equal(c32.astype(np.int64), colind + 1) and np.array_equal(v32, vals[:3])
+    import torch
+    o32 = rb.make_options(2, 5, n, 5, names[:3], index_base=1, index_width=32)
+    Xh = torch.from_numpy(X).pin_memory()
+    ch = torch.empty((N, n), dtype=torch.int32).pin_memory()
+    vh = torch.empty((3, N, n), dtype=torch.float64).pin_memory()
+    ctx._check(L.rbffd_generate_operator_host(ctx._h, C.byref(o32), Xh.data_ptr(), N, None, N, None, ch.data_ptr(), vh.data_ptr()))
+    assert np.array_equal(ch.numpy().astype(np.int64), colind + 1) and np.array_equal(vh.numpy(), vals[:3])
