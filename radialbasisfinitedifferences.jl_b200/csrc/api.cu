@@ -308,7 +308,11 @@ int rbffd_generate_operator_host(rbffd_context* ctx, const rbffd_options* opts, 
     const bool pinned = cudaPointerGetAttributes(&pa_c, colind_out) == cudaSuccess && pa_c.type == cudaMemoryTypeHost &&
                         cudaPointerGetAttributes(&pa_v, vals_out) == cudaSuccess && pa_v.type == cudaMemoryTypeHost;
     cudaGetLastError();
-    const int nchunks = 5;
+    constexpr int MAXCH = 8;
+    // RBFFD_HOST_CHUNKS (2..8) / RBFFD_HOST_CHUNK_RATIO: tuning knobs of the row-chunk pipeline (default: the measured optimum)
+    static const int nchunks_env = [] { const char* e = getenv("RBFFD_HOST_CHUNKS"); const int v = e ? atoi(e) : 0; return v >= 2 && v <= MAXCH ? v : 0; }();
+    static const double ratio_env = [] { const char* e = getenv("RBFFD_HOST_CHUNK_RATIO"); const double v = e ? atof(e) : 0.0; return v > 0.05 && v <= 1.0 ? v : 0.62; }();
+    const int nchunks = nchunks_env ? nchunks_env : 5;
     if (pinned && Y == X && M == N && M >= 64 * nchunks && !opts->sort_columns) {
         const bool trace = getenv("RBFFD_TRACE") != nullptr;
         const auto t_begin = std::chrono::steady_clock::now();
@@ -324,9 +328,14 @@ int rbffd_generate_operator_host(rbffd_context* ctx, const rbffd_options* opts, 
         RBFFD_TRY(rbffd_stencils_impl(ctx, dX.p, N, dim, dX.p, N, n, xgroup ? dG.p : nullptr, stencils.p, nullptr, nullptr, nullptr));
         // Row chunks shrink geometrically: big chunks first (few launch tails), small ones last (the copy of the last
         // chunk is the only one that nothing overlaps).
-        int64_t cbeg[nchunks + 1];
+        int64_t cbeg[MAXCH + 1];
         {
-            static const double frac[nchunks] = {0.38, 0.28, 0.18, 0.11, 0.05};
+            double frac[MAXCH] = {0.38, 0.28, 0.18, 0.11, 0.05, 0, 0, 0};
+            if (nchunks_env) {                                  // geometric: frac[k] ~ ratio^k
+                double tot = 0.0, w = 1.0;
+                for (int k = 0; k < nchunks; ++k) { frac[k] = w; tot += w; w *= ratio_env; }
+                for (int k = 0; k < nchunks; ++k) frac[k] /= tot;
+            }
             double acc = 0.0;
             cbeg[0] = 0;
             for (int k = 0; k < nchunks; ++k) {
@@ -341,11 +350,11 @@ int rbffd_generate_operator_host(rbffd_context* ctx, const rbffd_options* opts, 
         DevBuf<int> dflags;                        // status words of every chunk, inspected once at the end
         CUDA_TRY(ctx, c32.alloc((size_t)ch * n, st));
         CUDA_TRY(ctx, vb.alloc((size_t)M * n * nops, st));
-        CUDA_TRY(ctx, dflags.alloc(8 * nchunks, st));
+        CUDA_TRY(ctx, dflags.alloc(8 * MAXCH, st));
         // Declared after every temporary the copy stream reads, so it runs BEFORE their destructors on every exit path
         // (error returns included): the stream-ordered frees on `st` must not overtake D2H copies still in flight.
         struct DrainCopies { cudaStream_t s; ~DrainCopies() { cudaStreamSynchronize(s); } } drain_copies{ctx->copy_stream};
-        init_deferred_kernel<<<1, 8 * nchunks, 0, st>>>(dflags.p);
+        init_deferred_kernel<<<1, 8 * MAXCH, 0, st>>>(dflags.p);
         KLAUNCH(ctx);
         // The pattern crosses PCIe as int32 (half the bytes of the caller's int64) into a pinned staging buffer, slice by
         // slice; host threads widen every slice into colind_out as soon as its copy has landed, under the value copies.
@@ -479,7 +488,7 @@ int rbffd_generate_operator_host(rbffd_context* ctx, const rbffd_options* opts, 
         CUDA_TRY(ctx, cudaEventRecord(ctx->ev[1], st));
         lap("all chunks queued");
         ctx->deferred_flags = nullptr;
-        int hf[2 * nchunks];
+        int hf[2 * MAXCH];
         if (rc == RBFFD_OK) {
             DevBuf<int> packed;
             CUDA_TRY(ctx, packed.alloc(2 * nchunks, st));
