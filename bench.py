@@ -295,6 +295,8 @@ def main():
     phase = {"knn": 0.0, "weights": 0.0, "spmv": 0.0}
     shard = None
     t_shard = 0.0
+    # RBFFD_HALO=nccl: halo values travel by torch.distributed send/recv instead of peer-memory stores inside the product launch
+    use_nccl = world > 1 and os.environ.get("RBFFD_HALO", "p2p") == "nccl"
 
     if world == 1:
         NL = M = G ** dim
@@ -307,7 +309,7 @@ def main():
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         shard = sharding.Shard.lattice_block(ctx, dim, G, 0, blocks, rank, n)
-        shard.wire()
+        shard.wire(ipc=not use_nccl)
         torch.cuda.synchronize()
         t_shard = time.perf_counter() - t0
         M, NL = shard.n_owned, shard.n_owned + shard.n_halo
@@ -319,6 +321,13 @@ def main():
     u = torch.randn(M, dtype=torch.float64, device=dev)
     y = torch.empty(M, dtype=torch.float64, device=dev)
     op = ctx.operator_from_device(M, NL, n, r, colind.data_ptr(), vals.data_ptr())
+
+    def sharded_apply(o, xin, yout):
+        if use_nccl:
+            shard.exchange_collective(xin)                                     # RBFFD_HALO=nccl: pack -> NCCL send/recv -> unpack
+            shard.spmv_local_device(o, [0], [1.0], xin.data_ptr(), yout.data_ptr())
+        else:
+            shard.spmv_device(o, [0], [1.0], xin.data_ptr(), yout.data_ptr())  # ONE launch: push + interior rows + wait + boundary rows + ack
 
     def step(record):
         ev[0].record(stream)
@@ -333,7 +342,7 @@ def main():
                            Y_ptr=Q_ptr, M=M, center_ptr=center.data_ptr() if world == 1 else None, NS=M)
         ev[2].record(stream)
         if world > 1:
-            shard.spmv_device(op, [0], [1.0], u.data_ptr(), y.data_ptr())      # ONE launch: push + interior rows + wait + boundary rows + ack
+            sharded_apply(op, u, y)
         else:
             op.spmv_device(0, u.data_ptr(), y.data_ptr())
         ev[3].record(stream)
@@ -371,7 +380,7 @@ def main():
         u.copy_(full[:M])
         y_ref = torch.empty(M, dtype=torch.float64, device=dev)
         for rep in range(3):                                   # several epochs back to back
-            shard.spmv_device(op, [0], [1.0], u.data_ptr(), y.data_ptr())
+            sharded_apply(op, u, y)
         op.spmv_multi_device([0], [1.0], full.data_ptr(), y_ref.data_ptr())
         torch.cuda.synchronize()
         identical = bool(torch.equal(y, y_ref))
@@ -421,7 +430,7 @@ def main():
 
     def apply(o):
         if world > 1:
-            shard.spmv_device(o, [0], [1.0], u.data_ptr(), y2.data_ptr())
+            sharded_apply(o, u, y2)
         else:
             o.spmv_device(0, u.data_ptr(), y2.data_ptr())
     for i in range(6):
@@ -636,7 +645,7 @@ def main():
                        "l2": "every step writes %.0f MB of stencils+operator (> 126 MB L2), so no input survives in L2 between steps" % ((M * n * 4 * 2 + r * M * n * 8) / 1e6),
                        "parallelism": "spatial blocks %s, halo = stencil closure (%s nodes on rank 0), halo exchange: %s"
                                       % ("x".join(str(b) for b in blocks), "0" if world == 1 else str(NL - M),
-                                         "none" if world == 1 else "fused into the SpMV launch, NVLink peer stores into CUDA-IPC inboxes"),
+                                         "none" if world == 1 else ("NCCL send/recv (RBFFD_HALO=nccl)" if use_nccl else "fused into the SpMV launch, NVLink peer stores into CUDA-IPC inboxes")),
                        "global_nodes": total_nodes},
             "phases_ms": {"knn": phase["knn"] / K, "weights": phase["weights"] / K, "spmv(+halo)": phase["spmv"] / K},
             "roofline": {"kernel": "fused weight kernel (assemble + null-space elimination + solve + CSR write), flops by the LU convention (2/3)m^3 + 2m^2 r", "bound": "fp64",

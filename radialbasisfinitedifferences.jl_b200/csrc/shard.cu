@@ -83,12 +83,15 @@ template <int TPR, int NMAT, int VEC, int ITERS, int MODE>
 __global__ void __launch_bounds__(256) shard_spmv_kernel(ShardDev sd, int n, const int32_t* __restrict__ colind, SpmvMats m,
                                                          const double* __restrict__ x, SpmvEpilogue epi, double* __restrict__ y, int PB, int IB) {
     __shared__ unsigned s_epoch;
-    if (MODE == 0) {
+    const int b = blockIdx.x;
+    // only the push and the boundary-row CTAs take part in the exchange protocol (a few hundred of the grid's tens of
+    // thousands): the interior-row CTAs neither read the epoch nor touch a counter
+    const bool proto = MODE == 0 && (b < PB || b >= PB + IB);
+    if (proto) {
         if (threadIdx.x == 0) s_epoch = *reinterpret_cast<volatile unsigned*>(&sd.ctl->epoch) + 1u;
         __syncthreads();
     }
-    const unsigned ep = MODE == 0 ? s_epoch : 0u;
-    const int b = blockIdx.x;
+    const unsigned ep = proto ? s_epoch : 0u;
     if (b < PB) {
         // ---- push: this CTA moves one chunk of one peer's values ----
         int k = 0;
@@ -130,9 +133,10 @@ __global__ void __launch_bounds__(256) shard_spmv_kernel(ShardDev sd, int n, con
             }
         }
     }
-    if (MODE == 0) {
+    if (proto) {
         __syncthreads();
-        if (threadIdx.x == 0 && atomicAdd(&sd.ctl->all_done, 1u) == gridDim.x - 1u) {     // last CTA of the launch
+        // the last protocol CTA of the launch advances the epoch: every other one has read it by then
+        if (threadIdx.x == 0 && atomicAdd(&sd.ctl->all_done, 1u) == gridDim.x - (unsigned)IB - 1u) {
             sd.ctl->all_done = 0u;
             *reinterpret_cast<volatile unsigned*>(&sd.ctl->epoch) = ep;
         }

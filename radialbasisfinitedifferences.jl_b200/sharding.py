@@ -412,10 +412,11 @@ class Shard:
     def connect(self, peer, handle, fwd_offset, rev_offset, flags_offset):
         self.ctx._check(self.ctx._L.rbffd_shard_connect(self._h, peer, handle, int(fwd_offset), int(rev_offset), int(flags_offset)))
 
-    def wire(self, group=None):
+    def wire(self, group=None, ipc=True):
         """Collective over the ranks of `group` (rank r of the group = shard r): ships every rank's halo requests to the
         owners, allocates the CUDA-IPC inboxes and maps the peers' inboxes (NVLink peer stores).  torch.distributed is the
-        plumbing; a Julia host would do the same three steps over MPI."""
+        plumbing; a Julia host would do the same three steps over MPI.  ipc=False stops after the inbox allocation: the
+        halo values then travel through exchange_collective (no peer memory is mapped)."""
         import numpy as np
         import torch.distributed as dist
         want = {p: self.recv_ids(p) for p in range(self.nparts) if p != self.rank and self.recv_count(p) > 0}
@@ -425,6 +426,9 @@ class Shard:
             if p != self.rank and self.rank in allwant[p]:
                 self.set_send_ids(p, allwant[p][self.rank])
         mine = self.finalize()
+        if not ipc:
+            dist.barrier(group=group)
+            return
         everyone = [None] * self.nparts
         dist.all_gather_object(everyone, mine, group=group)
         for p in range(self.nparts):
@@ -483,6 +487,34 @@ class Shard:
 
     def tunpack_add_device(self, peer, buf_ptr, y_ptr):
         self.ctx._check(self.ctx._L.rbffd_shard_tunpack_add_device(self._h, peer, buf_ptr, y_ptr))
+
+    def exchange_collective(self, x, group=None):
+        """Forward halo exchange over torch.distributed point-to-point ops (NCCL send/recv over NVLink, gloo, ...) instead of
+        peer memory: pack -> batched isend/irecv -> unpack into the inbox.  Follow with spmv_local_device.  x: torch tensor of
+        the owned values.  The transport-agnostic alternative to the fused launch (e.g. no CUDA IPC between the ranks)."""
+        import torch
+        import torch.distributed as dist
+        ops, recv, keep = [], [], []
+        for p in range(self.nparts):
+            if p == self.rank:
+                continue
+            ns, nr = self.send_count(p), self.recv_count(p)
+            if ns:
+                sb = torch.empty(ns, dtype=torch.float64, device=x.device)
+                self.pack_device(p, x.data_ptr(), sb.data_ptr())
+                keep.append(sb)
+                ops.append(dist.P2POp(dist.isend, sb, p if group is None else dist.get_global_rank(group, p), group))
+            if nr:
+                rb_ = torch.empty(nr, dtype=torch.float64, device=x.device)
+                recv.append((p, rb_))
+                ops.append(dist.P2POp(dist.irecv, rb_, p if group is None else dist.get_global_rank(group, p), group))
+        if ops:
+            self.ctx.synchronize()                         # the packed values are complete before the transport reads them
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+        for p, rb_ in recv:
+            self.unpack_device(p, rb_.data_ptr())
+        self._bufs = keep + [r for _, r in recv]
 
     @staticmethod
     def exchange_local(shards, xs):

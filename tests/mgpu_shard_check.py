@@ -41,6 +41,13 @@ def check(ctx, rank, world, name, X, shard, p, polydeg, ops, dim, epochs=6):
         shard.spmv_device(op, which, coef, x.data_ptr(), y.data_ptr())
         gop.spmv_multi_device(which, coef, ug.data_ptr(), yg.data_ptr())
         assert torch.equal(y, yg[own]), f"{name}: sharded D*u differs from the single-GPU product"
+    # the same product over the torch.distributed transport (NCCL send/recv): pack -> isend/irecv -> unpack -> local product
+    ug = torch.from_numpy(fields[-1]).cuda()
+    x.copy_(ug[own])
+    shard.exchange_collective(x)
+    shard.spmv_local_device(op, which, coef, x.data_ptr(), y.data_ptr())
+    gop.spmv_multi_device(which, coef, ug.data_ptr(), yg.data_ptr())
+    assert torch.equal(y, yg[own]), f"{name}: sharded D*u over the collective transport differs"
     # CUDA-graph replay: the epoch lives in device memory, so the captured launch is replayable
     ug = torch.from_numpy(fields[0]).cuda()
     x.copy_(ug[own])
