@@ -106,10 +106,6 @@ __device__ __forceinline__ bool visible(int qg, int cg) {
     return true;                                     // interior + all boundary nodes (:24-28)
 }
 
-__device__ __forceinline__ bool lessp(double da, int ia, double db, int ib) {
-    return da < db || (da == db && ia < ib);
-}
-
 struct KnnArgs {
     Grid g;
     const double* xs;          // SoA sorted coordinates [D][N]

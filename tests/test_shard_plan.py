@@ -47,3 +47,16 @@ def test_plan_argument_errors():
         sharding.plan(X, 0)
     with pytest.raises(rb.RbffdError):
         sharding.plan(X, 17)
+
+
+def test_numa_binding_is_harmless_without_a_gpu():
+    """rb.bind_to_gpu_numa restricts the process to the cores next to its GPU (NVML); without NVML / a device it must change nothing"""
+    import os
+    before = os.sched_getaffinity(0)
+    n = rb.bind_to_gpu_numa(0)
+    after = os.sched_getaffinity(0)
+    assert isinstance(n, int) and n >= 0
+    assert after <= before and len(after) >= 1
+    if n == 0:
+        assert after == before
+    os.sched_setaffinity(0, before)
