@@ -361,7 +361,7 @@ __global__ void __launch_bounds__(128, MINB) weights_ns_kernel(NArgs a) {
         // 4 x 4 block pivots (nullspace.cuh): the pivot block is inverted in every lane and applied by DMMAs, operands change
         // fragment layout by SHFL -- no panel / pivot-row dumps through shared memory, one __syncwarp per block step
         __syncwarp();                                     // every lane is done with the Y tile: its first 256 B carry the pivot blocks
-        bad |= nsp::block_gj_warp<3, NJ, 4, 4>(c, nb, G, sgnbits);
+        bad |= nsp::block_gj_warp<3, NJ, 4, 4, true>(c, nb, G, sgnbits);
         // the matrix is now [I | y]  (right-hand-side column rcb + o lives in tile (rcb + o) / 8)
 #pragma unroll
         for (int I = 0; I < 3; ++I) {

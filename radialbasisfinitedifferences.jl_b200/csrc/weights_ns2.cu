@@ -997,7 +997,7 @@ __global__ void __launch_bounds__(32 * E1Cfg<D, Q, NT, NJ>::WARPS, E1Cfg<D, Q, N
                 const double2 v = __ldcs(reinterpret_cast<const double2*>(Sg + (J * NT + I) * 64 + 2 * lane));
                 c[I][J][0] = v.x; c[I][J][1] = v.y;
             }
-        const int bad = block_gj_warp<NT, NJ, NT, NJ>(c, nb, dsm, sgnbits);
+        const int bad = block_gj_warp<NT, NJ, NT, NJ, (NT * NJ <= 25)>(c, nb, dsm, sgnbits);
         if (bad < 0) *a.redo = 1;
         // the matrix is now [I | y]: y of operator o sits in column rcb + o
 #pragma unroll
