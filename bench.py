@@ -403,6 +403,8 @@ def main():
     t_end.record(stream)
     barrier()
     clocks.mark()
+    if shard is not None:
+        shard.check()                # a halo exchange that timed out (dead peer) is an error, not a number
     elapsed_ms = t_start.elapsed_time(t_end)
     launches = ctx.launch_count() - launches0
     clk = clocks.stop() if rank == 0 else None

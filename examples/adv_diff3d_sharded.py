@@ -150,6 +150,7 @@ def run(g, steps, alpha=2e-3, a=(0.3, 0.2, 0.1), bw=None, cfl=0.08, combine=True
     ev1.record()
     torch.cuda.synchronize()
     t_run = ev0.elapsed_time(ev1) * 1e-3
+    shard.check()                                    # a halo exchange that timed out waiting for a peer is an error
     if world > 1:
         dist.barrier()
     t = steps * dt

@@ -271,6 +271,9 @@ int rbffd_shard_create_device(rbffd_context* ctx, int32_t dim, int32_t n, const 
                               int64_t nc, const double* box_lo, const double* box_hi, int32_t rank, int32_t nparts, rbffd_shard** shard);
 int rbffd_shard_destroy(rbffd_shard* shard);
 int rbffd_shard_info(const rbffd_shard* shard, int64_t* n_owned, int64_t* n_interior, int64_t* n_halo);
+/* synchronises the context's stream and returns RBFFD_ERR_HALO when a fused exchange gave up waiting for a peer (the waits inside
+ * the kernels time out after 20 s instead of hanging the GPU: crashed rank, mismatched call sequence), RBFFD_OK otherwise */
+int rbffd_shard_status(rbffd_shard* shard);
 /* local id -> global id, n_owned + n_halo entries */
 int rbffd_shard_global_ids_host(rbffd_shard* shard, int32_t index_base, int64_t* gid_out);
 /* device arrays of the shard: coordinates [n_owned + n_halo][dim] and stencils [n_owned][n] (local ids, entry 0 = the row's node):

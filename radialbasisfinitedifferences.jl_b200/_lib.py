@@ -118,6 +118,7 @@ _SIGNATURES = {
     "rbffd_shard_create_host": ([_vp, _vp, _i64, _i32, _vp, _i32, _i32, _i32, C.POINTER(_vp)], C.c_int),
     "rbffd_shard_create_device": ([_vp, _i32, _i32, _vp, _vp, _vp, _i64, _vp, _vp, _i32, _i32, C.POINTER(_vp)], C.c_int),
     "rbffd_shard_destroy": ([_vp], C.c_int),
+    "rbffd_shard_status": ([_vp], C.c_int),
     "rbffd_shard_info": ([_vp, C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i64)], C.c_int),
     "rbffd_shard_global_ids_host": ([_vp, _i32, _vp], C.c_int),
     "rbffd_shard_device_arrays": ([_vp, C.POINTER(_vp), C.POINTER(_vp)], C.c_int),

@@ -41,6 +41,7 @@ constexpr int F_WORDS = 4 * MAXP;
 struct ShardCtl {                           // plain device memory of the owning rank
     unsigned epoch, tepoch;                 // completed forward / reverse exchanges
     unsigned bdone, all_done;
+    unsigned timed_out;                     // a wait for a peer gave up (see spin_until)
     unsigned push_done[MAXP], tpush_done[MAXP];
 };
 
@@ -72,8 +73,25 @@ __device__ __forceinline__ unsigned ld_acquire_sys_u32(const unsigned* p) {
 __device__ __forceinline__ void st_release_sys_u32(unsigned* p, unsigned v) {
     asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
-__device__ __forceinline__ void spin_until(const unsigned* flag, unsigned value) {
-    while ((int)(ld_acquire_sys_u32(flag) - value) < 0) { }
+// Waits for a peer's epoch flag.  A peer that never arrives (crashed process, mismatched call sequence) must not hang the GPU:
+// after SPIN_TIMEOUT_NS the wait gives up, records the fact in the control block (rbffd_shard_status reports it as an error)
+// and the launch runs to completion with whatever the inbox holds.
+constexpr unsigned long long SPIN_TIMEOUT_NS = 20ull * 1000ull * 1000ull * 1000ull;
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ void spin_until(const unsigned* flag, unsigned value, unsigned* timed_out) {
+    unsigned long long t0 = 0;
+    unsigned spins = 0;
+    while ((int)(ld_acquire_sys_u32(flag) - value) < 0) {
+        if ((++spins & 1023u) == 0u) {
+            const unsigned long long now = global_ns();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > SPIN_TIMEOUT_NS) { *timed_out = 1u; return; }
+        }
+    }
 }
 
 // ---- sharded SpMV, halo exchange fused ------------------------------------------------------------------------------
@@ -98,7 +116,7 @@ __global__ void __launch_bounds__(256) shard_spmv_kernel(ShardDev sd, int n, con
         while (b >= sd.chunk_off[k + 1]) ++k;
         const long long e0 = sd.send_off[k] + (long long)(b - sd.chunk_off[k]) * PUSH_CHUNK;
         const long long e1 = min(sd.send_off[k + 1], e0 + PUSH_CHUNK);
-        if (threadIdx.x == 0) spin_until(sd.flags + F_ACK + sd.send_peer[k], ep - 1u);     // the peer is done with the previous epoch
+        if (threadIdx.x == 0) spin_until(sd.flags + F_ACK + sd.send_peer[k], ep - 1u, &sd.ctl->timed_out);     // the peer is done with the previous epoch
         __syncthreads();
         double* dst = sd.send_dst[k] - sd.send_off[k];
         for (long long i = e0 + threadIdx.x; i < e1; i += 256) dst[i] = x[sd.send_idx[i]];
@@ -117,7 +135,7 @@ __global__ void __launch_bounds__(256) shard_spmv_kernel(ShardDev sd, int n, con
         spmv_rows<TPR, NMAT, VEC, ITERS, false>(warp, 0, sd.n_int, n, colind, m, x, nullptr, 0, epi, y);
     } else {
         if (MODE == 0) {
-            if ((int)threadIdx.x < sd.nrecv) spin_until(sd.flags + F_READY + sd.recv_peer[threadIdx.x], ep);
+            if ((int)threadIdx.x < sd.nrecv) spin_until(sd.flags + F_READY + sd.recv_peer[threadIdx.x], ep, &sd.ctl->timed_out);
             __syncthreads();
         }
         const int64_t warp = ((int64_t)(b - PB - IB) * 256 + threadIdx.x) >> 5;
@@ -154,7 +172,7 @@ __global__ void __launch_bounds__(256) shard_tpush_kernel(ShardDev sd, const dou
     while (b >= sd.rchunk_off[r + 1]) ++r;
     const long long e0 = sd.recv_off[r] + (long long)(b - sd.rchunk_off[r]) * PUSH_CHUNK;
     const long long e1 = min(sd.recv_off[r + 1], e0 + PUSH_CHUNK);
-    if (threadIdx.x == 0) spin_until(sd.flags + F_TACK + sd.recv_peer[r], ep - 1u);
+    if (threadIdx.x == 0) spin_until(sd.flags + F_TACK + sd.recv_peer[r], ep - 1u, &sd.ctl->timed_out);
     __syncthreads();
     double* dst = sd.recv_rdst[r] - sd.recv_off[r];
     for (long long i = e0 + threadIdx.x; i < e1; i += 256) dst[i] = text[sd.n_owned + i];
@@ -181,7 +199,7 @@ __global__ void __launch_bounds__(256) shard_tcombine_kernel(ShardDev sd, int k,
     __shared__ unsigned s_epoch;
     if (threadIdx.x == 0) {
         s_epoch = *reinterpret_cast<volatile unsigned*>(&sd.ctl->tepoch) + 1u;
-        spin_until(sd.flags + F_TREADY + sd.send_peer[k], s_epoch);
+        spin_until(sd.flags + F_TREADY + sd.send_peer[k], s_epoch, &sd.ctl->timed_out);
     }
     __syncthreads();
     const long long i = sd.send_off[k] + blockIdx.x * (long long)blockDim.x + threadIdx.x;
@@ -675,6 +693,17 @@ int rbffd_shard_destroy(rbffd_shard* s) {
     if (s->ctl) cudaFree(s->ctl);
     if (s->text) cudaFree(s->text);
     delete s;
+    return RBFFD_OK;
+}
+
+int rbffd_shard_status(rbffd_shard* s) {
+    if (!s) return RBFFD_ERR_INVALID;
+    rbffd_context* ctx = s->ctx;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    unsigned flag = 0;
+    CUDA_TRY(ctx, cudaMemcpyAsync(&flag, &s->ctl->timed_out, sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    if (flag) RBFFD_FAIL(ctx, RBFFD_ERR_HALO, "shard %d: a halo exchange timed out waiting for a peer (crashed rank or mismatched sequence of rbffd_shard_spmv* calls); results since then are invalid", s->rank);
     return RBFFD_OK;
 }
 

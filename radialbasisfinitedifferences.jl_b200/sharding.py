@@ -356,6 +356,10 @@ class Shard:
         except Exception:
             pass
 
+    def check(self):
+        """synchronise and raise RbffdError(ERR_HALO) if a fused halo exchange timed out waiting for a peer"""
+        self.ctx._check(self.ctx._L.rbffd_shard_status(self._h))
+
     def global_ids(self, index_base=0):
         import numpy as np
         out = np.empty(self.n_owned + self.n_halo, np.int64)

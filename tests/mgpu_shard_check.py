@@ -81,6 +81,7 @@ def check(ctx, rank, world, name, X, shard, p, polydeg, ops, dim, epochs=6):
         ctx.synchronize()
         got = y.cpu().numpy()
         assert np.all(np.abs(got - ref[g[:shard.n_owned]]) <= 1e-13 * bound[g[:shard.n_owned]] + 1e-300), f"{name}: sharded E'*v differs"
+    shard.check()                                      # no exchange timed out
     dist.barrier()
     if rank == 0:
         print(f"{name}: world {world}, N {N}, rank 0 owns {shard.n_owned} ({shard.n_interior} interior) + {shard.n_halo} halo: bit-identical", flush=True)

@@ -86,6 +86,8 @@ def _check_partition(ctx, X, part, nparts, p, n, polydeg, ops, shards=None):
     for s, y, g in zip(shards, ys, gids):
         got = y.cpu().numpy()
         assert np.all(np.abs(got - ref[g[:s.n_owned]]) <= 1e-13 * bound[g[:s.n_owned]] + 1e-300), "sharded E'*v differs"
+    for s in shards:
+        s.check()
     for op in lops:
         op.close()
     if not own:
