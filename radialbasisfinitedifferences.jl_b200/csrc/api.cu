@@ -455,8 +455,9 @@ int rbffd_generate_operator_host(rbffd_context* ctx, const rbffd_options* opts, 
         double t_weights = 0.0;
         int rc = RBFFD_OK;
         ctx->trusted_stencils = true;              // produced by our own search: no range check per chunk
+        ctx->collocated_rows = true;               // Y == X: row r0 + i sits at the centre of stencil r0 + i
         ctx->deferred_flags = dflags.p;            // no host synchronisation per chunk: the kernels queue back to back
-        struct Restore { rbffd_context* c; ~Restore() { c->deferred_flags = nullptr; c->trusted_stencils = false; } } restore{ctx};
+        struct Restore { rbffd_context* c; ~Restore() { c->deferred_flags = nullptr; c->trusted_stencils = false; c->collocated_rows = false; } } restore{ctx};
         std::vector<cudaEvent_t>& cev = wd.chunk_done;
         CUDA_TRY(ctx, cudaEventRecord(ctx->ev[0], st));
         const bool dbg_noship = getenv("RBFFD_DEBUG_NOSHIP") != nullptr;     // timing experiments only: results stay on the device

@@ -23,6 +23,7 @@ struct rbffd_context {
     int* hflags = nullptr;       // 16 ints of mapped pinned host memory: status words are published with plain stores from a
     int* hflags_dev = nullptr;   // tiny kernel, never by a D2H memcpy (that would queue behind bulk D2H traffic on the copy engine)
     bool trusted_stencils = false;   // set by internal callers whose stencils come from our own search (skips range checks)
+    bool collocated_rows = false;    // set by internal callers whose row i is evaluated AT the centre of stencil i (eta == 0 exactly)
     long long launches = 0;      // hand-written kernels launched through this context (rbffd_launch_count)
     // deferred status checks (host entry point): when set, the weight path writes its status words of the current row
     // chunk to deferred_flags[8 * deferred_slot ..] ([0] singular node + 1, [4] null-space kernel refused) and never

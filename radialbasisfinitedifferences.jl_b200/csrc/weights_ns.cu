@@ -95,7 +95,11 @@ __host__ __device__ constexpr int lap_col(int a) {
     return D == 2 ? (Q > 3 ? (a == 0 ? 3 : 5) : -1) : (Q > 4 ? (a == 0 ? 4 : (a == 1 ? 7 : 9)) : -1);
 }
 
-template <int D, int Q, int MINB, bool FOLD>
+// NN, NO != 0: stencil size and operator count fixed at compile time (the BASELINE configs[1] shape n = 30, one operator):
+// the column classification of the Y tile, the padding tests, the block-step guards and the back-substitution trip counts
+// then fold to constants.
+// PP != 0: PHS power fixed; COLLOC: every row is evaluated at its own stencil centre (Y == X, no centre indirection), so eta == 0.
+template <int D, int Q, int MINB, bool FOLD, int NN = 0, int NO = 0, int PP = 0, bool COLLOC = false>
 __global__ void __launch_bounds__(128, MINB) weights_ns_kernel(NArgs a) {
     constexpr int LD = NS_LD, US = NS_US;
     constexpr int KS = (Q + 3) / 4, QP = 4 * KS;      // k-steps of the DMMAs over the basic nodes
@@ -103,7 +107,7 @@ __global__ void __launch_bounds__(128, MINB) weights_ns_kernel(NArgs a) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = lane >> 2, t = lane & 3;
     const OpTables& T = a.T;
-    const int n = T.n, nops = T.nops, nb = n - Q, BS = a.bs;
+    const int n = NN ? NN : T.n, nops = NO ? NO : T.nops, nb = n - Q, BS = NO ? ((NO + 1) & ~1) : a.bs;
     double* G = reinterpret_cast<double*>(nsm + (size_t)warp * a.smem_per_warp);   // Phi~ (stride LD), then Y, then [S|t]
     double* Yb = G;                                   // aliases G: written only after every read of Phi~ is done
     double* Wt = G + 32 * US;                         // [32][QP]: W' rows of the non-basic nodes, then the w_p rows
@@ -114,8 +118,9 @@ __global__ void __launch_bounds__(128, MINB) weights_ns_kernel(NArgs a) {
     int* perm = reinterpret_cast<int*>(Sc + 32 * DP);
     const double EPS = 2.220446049250313e-16;
     const unsigned FULL = 0xffffffffu;
-    const double sgn = (((T.p + 1) >> 1) & 1) ? -1.0 : 1.0;       // (-1)^((p+1)/2) S is positive definite
-    const int hp = (T.p - 1) >> 1;
+    const int pw = PP ? PP : T.p;
+    const double sgn = (((pw + 1) >> 1) & 1) ? -1.0 : 1.0;        // (-1)^((p+1)/2) S is positive definite
+    const int hp = (pw - 1) >> 1;
     const int sgnbits = sgn < 0.0 ? (int)0x80000000 : 0;
     // right-hand-side columns: in the spare columns of the last null-space tile when they fit, else in a 4th tile column
     const int rc0 = (nb + 3) & ~3;
@@ -148,8 +153,11 @@ __global__ void __launch_bounds__(128, MINB) weights_ns_kernel(NArgs a) {
             sx[c] = xv - xc;
             s[c] = 1.0 / warp_max_nonneg(fabs(sx[c]));
             sx[c] = sx[c] * s[c];
-            eta[c] = (a.Y[i * D + c] - xc) * s[c];
-            eta_zero = eta_zero && (eta[c] == 0.0);
+            if constexpr (COLLOC) eta[c] = 0.0;
+            else {
+                eta[c] = (a.Y[i * D + c] - xc) * s[c];
+                eta_zero = eta_zero && (eta[c] == 0.0);
+            }
         }
         // ---- 1. column reduction of [P; g']: lane l < n holds row l of P, lane n+o (or registers grow) the row g_o' ----
         double prow[Q], grow[Q];
@@ -356,7 +364,7 @@ __global__ void __launch_bounds__(128, MINB) weights_ns_kernel(NArgs a) {
         //         static pivot rows (row 4kb+s), so no pivot search, no row selects and a static pivot-row dump ----
         if (i + istride < a.NS) {
             asm volatile("prefetch.global.L1 [%0];" ::"l"(a.X + (int64_t)id_next * D));
-            if (lane < D) asm volatile("prefetch.global.L1 [%0];" ::"l"(a.Y + (i + istride) * D + lane));
+            if (!COLLOC && lane < D) asm volatile("prefetch.global.L1 [%0];" ::"l"(a.Y + (i + istride) * D + lane));
         }
         // 4 x 4 block pivots (nullspace.cuh): the pivot block is inverted in every lane and applied by DMMAs, operands change
         // fragment layout by SHFL -- no panel / pivot-row dumps through shared memory, one __syncwarp per block step
@@ -423,6 +431,13 @@ int launch_ns(rbffd_context* ctx, NArgs& a) {
     const bool fold = ((nb + 3) & ~3) + a.T.nops <= NS_NB;
     auto kern = four ? (fold ? weights_ns_kernel<D, Q, 4, true> : weights_ns_kernel<D, Q, 4, false>)
                      : (fold ? weights_ns_kernel<D, Q, 3, true> : weights_ns_kernel<D, Q, 3, false>);
+    if constexpr (D == 2 && Q == 10) {
+        static const bool no_spec = [] { const char* e = getenv("RBFFD_NS_SPECIALIZE"); return e && atoi(e) == 0; }();
+        if (four && fold && a.T.n == 30 && a.T.nops == 1 && !no_spec) {
+            const bool colloc = a.center == nullptr && (a.Y == a.X || ctx->collocated_rows);      // row i is evaluated at the centre of stencil i
+            kern = (a.T.p == 5 && colloc) ? weights_ns_kernel<2, 10, 4, true, 30, 1, 5, true> : weights_ns_kernel<2, 10, 4, true, 30, 1>;
+        }
+    }
     CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t blocks_needed = (a.NS + 3) / 4;
     // CTAs per resident slot: many short CTAs balance better than a few long grid-stride loops and keep the concurrently
