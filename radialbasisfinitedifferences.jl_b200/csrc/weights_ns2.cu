@@ -343,7 +343,10 @@ __device__ __forceinline__ void phs_assemble_half(const double* __restrict__ Sc,
     }
 }
 
-template <int D, int Q, int NT, int NJ, bool SPLIT>
+// NN, NO != 0: stencil size and operator count fixed at compile time (the BASELINE configs[2] and configs[3] shapes): the column
+// classification of the Y tile, the padding tests, the block-step guards and the trip counts of the node and store phases fold
+// to constants (before, 45 % of this kernel's instructions were index arithmetic and predicates on run-time n, n - q, r).
+template <int D, int Q, int NT, int NJ, bool SPLIT, int NN = 0, int NO = 0>
 __global__ void __launch_bounds__(128, 4) ns2_solve_kernel(Ns2Args a) {
     using C = SvCfg<D, Q, NT, NJ>;
     constexpr int LD = SV_LD, KS = C::KS, US = C::US, DP = C::DP, NBP = C::NBP, JJ = C::JJ, WS = C::WS;
@@ -351,7 +354,7 @@ __global__ void __launch_bounds__(128, 4) ns2_solve_kernel(Ns2Args a) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, t = lane & 3;
     const OpTables& T = a.T;
-    const int n = T.n, nops = T.nops, nb = n - Q, BS = a.bs;
+    const int n = NN ? NN : T.n, nops = NO ? NO : T.nops, nb = n - Q, BS = NO ? (NO > 6 ? ((NO + 1) & ~1) : 6) : a.bs;
     double* G = reinterpret_cast<double*>(wsm);
     double* Yb = G;
     double* Wt = G + C::G;                            // [Q][WS]
@@ -366,7 +369,7 @@ __global__ void __launch_bounds__(128, 4) ns2_solve_kernel(Ns2Args a) {
     const double sgn = (((T.p + 1) >> 1) & 1) ? -1.0 : 1.0;           // (-1)^((p+1)/2) S is positive definite
     const int sgnbits = sgn < 0.0 ? (int)0x80000000 : 0;
     const int hp = (T.p - 1) >> 1;
-    const int rcb = a.rcb;                            // first right-hand-side column; also the position of w_p in Wt
+    const int rcb = NN ? (NJ == NT ? ((NN - Q + 3) & ~3) : 8 * NT) : a.rcb;      // first right-hand-side column; also the position of w_p in Wt
     const int NR = (n + 7) >> 3;                      // row tiles of Y
     // exchange buffers of the elimination (alias the Y tile), alternating by block-step parity
     constexpr int PS = 52, UST = 8 * NJ + 4;          // strides == 4 (mod 16)
@@ -959,7 +962,7 @@ struct E1Cfg {
     static constexpr int MINB = NT * NJ > 25 ? 4 : 3;                     // CTAs per SM the register budget is set for
 };
 
-template <int D, int Q, int NT, int NJ>
+template <int D, int Q, int NT, int NJ, int NN = 0, int NO = 0>
 __global__ void __launch_bounds__(32 * E1Cfg<D, Q, NT, NJ>::WARPS, E1Cfg<D, Q, NT, NJ>::MINB) ns2_elim1_kernel(Ns2Args a) {
     using C = E1Cfg<D, Q, NT, NJ>;
     constexpr int NBP = C::NBP, WS = C::WS, NW = C::WARPS;
@@ -967,7 +970,7 @@ __global__ void __launch_bounds__(32 * E1Cfg<D, Q, NT, NJ>::WARPS, E1Cfg<D, Q, N
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = lane >> 2, t = lane & 3;
     const OpTables& T = a.T;
-    const int n = T.n, nops = T.nops, nb = n - Q;
+    const int n = NN ? NN : T.n, nops = NO ? NO : T.nops, nb = n - Q;
     double* base = reinterpret_cast<double*>(esm + (size_t)warp * C::BYTES);
     double* dsm = base;                               // [2][16] pivot blocks
     double* Wt = dsm + C::DSM;                        // [Q][WS]
@@ -977,7 +980,7 @@ __global__ void __launch_bounds__(32 * E1Cfg<D, Q, NT, NJ>::WARPS, E1Cfg<D, Q, N
     int* perm = reinterpret_cast<int*>(pf + C::PF);   // [64]
     const double sgn = (((T.p + 1) >> 1) & 1) ? -1.0 : 1.0;
     const int sgnbits = sgn < 0.0 ? (int)0x80000000 : 0;
-    const int rcb = a.rcb;
+    const int rcb = NN ? (NJ == NT ? ((NN - Q + 3) & ~3) : 8 * NT) : a.rcb;
     for (int64_t i = (int64_t)blockIdx.x * NW + warp; i < a.cnt; i += (int64_t)gridDim.x * NW) {
         const int64_t row = a.row0 + i;
         const unsigned char* rec = a.rec + i * a.rec_stride;
@@ -1072,11 +1075,26 @@ __global__ void __launch_bounds__(32 * E1Cfg<D, Q, NT, NJ>::WARPS, E1Cfg<D, Q, N
     }
 }
 
+// shapes with compile-time (n, operator count): BASELINE configs[2] (2-D, n = 50, degree 4, four operators) and configs[3] / [4]
+// (3-D, n = 60, degree 3, four operators).  RBFFD_NS2_SPECIALIZE = bit mask (1 solve, 2 elimination; 0 keeps the generic instances: A/B comparisons).
+template <int D, int Q, int NT, int NJ>
+struct Ns2Shape {
+    static constexpr bool cfg3 = D == 2 && Q == 15 && NT == 5 && NJ == 5;
+    static constexpr bool cfg4 = D == 3 && Q == 20 && NT == 5 && NJ == 6;
+    static constexpr int NN = cfg3 ? 50 : (cfg4 ? 60 : 0), NO = (cfg3 || cfg4) ? 4 : 0;
+    static bool matches(const OpTables& T, int which) {       // which: 1 = solve kernel, 2 = elimination kernel (bit mask in the env)
+        static const int mask = [] { const char* e = getenv("RBFFD_NS2_SPECIALIZE"); return e ? atoi(e) : 3; }();
+        return NN != 0 && (mask & which) && T.n == NN && T.nops == NO;
+    }
+};
+
 template <int D, int Q, int NT, int NJ>
 int launch_elim1(rbffd_context* ctx, Ns2Args& a) {
     using C = E1Cfg<D, Q, NT, NJ>;
+    using SH = Ns2Shape<D, Q, NT, NJ>;
     const size_t smem = (size_t)C::BYTES * C::WARPS;
     auto kern = ns2_elim1_kernel<D, Q, NT, NJ>;
+    if constexpr (SH::NN != 0) { if (SH::matches(a.T, 2)) kern = ns2_elim1_kernel<D, Q, NT, NJ, SH::NN, SH::NO>; }
     CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 1;
     CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32 * C::WARPS, smem));
@@ -1115,6 +1133,8 @@ int launch_solve(rbffd_context* ctx, Ns2Args& a) {
     if ((int64_t)smem_launch > ctx->max_smem_optin) return RBFFD_ERR_UNSUPPORTED;
     const bool split = a.stile != nullptr && NT <= 5;
     auto kern = split ? ns2_solve_kernel<D, Q, NT, NJ, (NT <= 5)> : ns2_solve_kernel<D, Q, NT, NJ, false>;
+    using SH = Ns2Shape<D, Q, NT, NJ>;
+    if constexpr (SH::NN != 0) { if (split && SH::matches(a.T, 1)) kern = ns2_solve_kernel<D, Q, NT, NJ, true, SH::NN, SH::NO>; }
     CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_launch));
     const int per_sm = std::max<int>(1, std::min<int>(4, (int)((228 * 1024) / (smem_launch + 1024))));
     static const int waves = [] { const char* e = getenv("RBFFD_NSW_WAVES"); const int w = e ? atoi(e) : 0; return w > 0 ? w : 256; }();
