@@ -81,7 +81,7 @@ __device__ unsigned long long ns2_prof[16];
 // ---------------------------------------------------------------------------------------------------------------------
 // stage A: pivoted column reduction of [P; g'], one warp per stencil, rows `lane` and `lane + 32`
 // ---------------------------------------------------------------------------------------------------------------------
-template <int D, int Q>
+template <int D, int Q, int NN = 0, int NO = 0>
 __global__ void __launch_bounds__(128, 4) ns2_pred_kernel(Ns2Args a) {
     constexpr int KS = (Q + 3) / 4, QP = 4 * KS;
     constexpr int CS = (Q + 2) & ~1;                  // published row: Q entries + the reciprocal of the pivot, even
@@ -90,7 +90,7 @@ __global__ void __launch_bounds__(128, 4) ns2_pred_kernel(Ns2Args a) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned FULL = 0xffffffffu;
     const OpTables& T = a.T;
-    const int n = T.n, nops = T.nops, nb = n - Q;
+    const int n = NN ? NN : T.n, nops = NO ? NO : T.nops, nb = n - Q;      // NN, NO != 0: compile-time shape (see ns2_solve_kernel)
     double* cand = &cand_s[warp][0][0];
     double* stage = &stage_s[warp][0];
     const int slot0 = lane, slot1 = lane + 32;
@@ -243,20 +243,36 @@ __global__ void __launch_bounds__(128, 4) ns2_pred_kernel(Ns2Args a) {
 // ---------------------------------------------------------------------------------------------------------------------
 constexpr int SV_LD = 68;      // row stride of Phi~; == 4 (mod 16): pair stores 69 l + k, 69 l + 68 k and fragment loads 68 g + t conflict-free
 
-template <int D, int Q, int NT, int NJ>
+#ifndef NS2_CFG3_MINB
+#define NS2_CFG3_MINB 6
+#endif
+#ifndef NS2_CFG4_MINB
+#define NS2_CFG4_MINB 5
+#endif
+template <int D, int Q, int NT, int NJ, int NN = 0, int NO = 0>
 struct SvCfg {
     static constexpr int KS = (Q + 3) / 4;
+    // compile-time n: the Phi~ tile shrinks to the stencil -- row stride = the smallest value >= n that is == 4 (mod 16), n rows
+    // (the fragment loads of the padded rows n .. 8 NR - 1 run on into the W' block: finite garbage that stays in padded rows of
+    // Y), and the RBF right-hand sides move into the spare columns n .. LD - 1 of the tile when they fit.  Shared memory per
+    // CTA: 46.0 -> 34.5 KB at n = 50 (6 CTAs per SM), 50.6 -> 45.3 KB at n = 60 (5 CTAs per SM).
+    static constexpr int LD = NN ? ((NN + 11) / 16) * 16 + 4 : SV_LD;
+    static constexpr int BSC = NO > 6 ? ((NO + 1) & ~1) : 6;      // row stride of a separate right-hand-side tile (Ys aliases it)
+    static constexpr bool BTG = NN != 0 && NO != 0 && LD - NN >= NO;      // right-hand sides in the spare columns of Phi~
+    static constexpr int MINB = NN == 0 ? 4 : (LD < SV_LD ? NS2_CFG3_MINB : (BTG ? NS2_CFG4_MINB : 4));
     static constexpr int NBP = 8 * NT;                    // padded null-space dimension
     static constexpr int US = ((8 * NJ + 15) & ~15) + 4;  // row stride of the Y tile, == 4 (mod 16)
     static constexpr int DP = D == 2 ? 2 : 4;
     static constexpr int JJ = NJ > 4 ? 2 : 1;             // tile columns of [S | t] per warp (column J lives in warp J % 4)
     static constexpr int WS = 8 * NJ + 4;                 // row stride of the transposed W' block, == 4 or 12 (mod 16)
-    static constexpr int G = 64 * SV_LD;                  // Phi~, later the Y tile, later the exchange buffers of the elimination
+    static constexpr int NRT = NN ? (NN + 7) / 8 : 8;     // row tiles of Y
+    static constexpr int G = NN ? (NN * LD > 8 * NRT * US ? NN * LD : 8 * NRT * US) : 64 * SV_LD;     // Phi~, later the Y tile, later the exchange buffers of the elimination
     static constexpr int WT = Q * WS;                     // W'^T: [monomial][position], the w_p entries at positions rcb ..
     static constexpr int SC = 64 * DP;
     static constexpr int HDR = NS2_REC_HDR / 8;           // header of the NEXT record (prefetched)
     static constexpr int XN = 64 * D;                     // node coordinates of the NEXT stencil by position (prefetched)
-    static_assert(64 * US <= G, "Y tile must fit into the Phi tile");
+    static_assert(8 * NRT * US <= G && LD >= (NN ? NN : 64), "Y tile must fit into the Phi tile");
+    static_assert(NN == 0 || 8 * NRT * LD <= G + Q * WS, "fragment loads of the padded rows must stay inside the W' block");
     static_assert(NJ == NT || NJ == NT + 1, "right-hand sides ride in the last null-space tile column or in one more");
 };
 
@@ -347,21 +363,22 @@ __device__ __forceinline__ void phs_assemble_half(const double* __restrict__ Sc,
 // classification of the Y tile, the padding tests, the block-step guards and the trip counts of the node and store phases fold
 // to constants (before, 45 % of this kernel's instructions were index arithmetic and predicates on run-time n, n - q, r).
 template <int D, int Q, int NT, int NJ, bool SPLIT, int NN = 0, int NO = 0>
-__global__ void __launch_bounds__(128, 4) ns2_solve_kernel(Ns2Args a) {
-    using C = SvCfg<D, Q, NT, NJ>;
-    constexpr int LD = SV_LD, KS = C::KS, US = C::US, DP = C::DP, NBP = C::NBP, JJ = C::JJ, WS = C::WS;
+__global__ void __launch_bounds__(128, (SvCfg<D, Q, NT, NJ, NN, NO>::MINB)) ns2_solve_kernel(Ns2Args a) {
+    using C = SvCfg<D, Q, NT, NJ, NN, NO>;
+    static_assert(NN == 0 || SPLIT, "the shrunk Phi~ tile has no room for the exchange buffers of the in-kernel elimination");
+    constexpr int LD = C::LD, KS = C::KS, US = C::US, DP = C::DP, NBP = C::NBP, JJ = C::JJ, WS = C::WS;
     extern __shared__ __align__(16) unsigned char wsm[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, t = lane & 3;
     const OpTables& T = a.T;
-    const int n = NN ? NN : T.n, nops = NO ? NO : T.nops, nb = n - Q, BS = NO ? (NO > 6 ? ((NO + 1) & ~1) : 6) : a.bs;
+    const int n = NN ? NN : T.n, nops = NO ? NO : T.nops, nb = n - Q, BS = C::BTG ? LD : (NO ? C::BSC : a.bs);
     double* G = reinterpret_cast<double*>(wsm);
     double* Yb = G;
     double* Wt = G + C::G;                            // [Q][WS]
     double* Sc = Wt + C::WT;
-    double* Bt = Sc + C::SC;                          // [64][BS] RBF right-hand sides by position
-    double* Ys = Bt;                                  // solution y, [op][NBP] (Bt is dead by then; 8 * 48 <= 64 * BS needs BS >= 6)
-    double* pf = Bt + 64 * BS;                        // [8] chain-rule factor of every operator
+    double* Bt = C::BTG ? G + NN : Sc + C::SC;        // [64][BS] RBF right-hand sides by position (BTG: columns n .. of the Phi~ rows)
+    double* Ys = Bt;                                  // solution y, [op][NBP] (Bt is dead by then; 8 * 48 <= 64 * BS needs BS >= 6; not with BTG)
+    double* pf = C::BTG ? Sc + C::SC : Bt + 64 * BS;  // [8] chain-rule factor of every operator
     double* hdr = pf + 8;                             // header of the next record
     double* Xn = hdr + C::HDR;                        // [64][D] coordinates of the next stencil's nodes
     int* perm = reinterpret_cast<int*>(Xn + C::XN);   // [64] position -> stencil slot
@@ -1076,14 +1093,14 @@ __global__ void __launch_bounds__(32 * E1Cfg<D, Q, NT, NJ>::WARPS, E1Cfg<D, Q, N
 }
 
 // shapes with compile-time (n, operator count): BASELINE configs[2] (2-D, n = 50, degree 4, four operators) and configs[3] / [4]
-// (3-D, n = 60, degree 3, four operators).  RBFFD_NS2_SPECIALIZE = bit mask (1 solve, 2 elimination; 0 keeps the generic instances: A/B comparisons).
+// (3-D, n = 60, degree 3, four operators).  RBFFD_NS2_SPECIALIZE = bit mask (1 solve, 2 elimination, 4 column reduction; 0 keeps the generic instances: A/B comparisons).
 template <int D, int Q, int NT, int NJ>
 struct Ns2Shape {
     static constexpr bool cfg3 = D == 2 && Q == 15 && NT == 5 && NJ == 5;
     static constexpr bool cfg4 = D == 3 && Q == 20 && NT == 5 && NJ == 6;
     static constexpr int NN = cfg3 ? 50 : (cfg4 ? 60 : 0), NO = (cfg3 || cfg4) ? 4 : 0;
-    static bool matches(const OpTables& T, int which) {       // which: 1 = solve kernel, 2 = elimination kernel (bit mask in the env)
-        static const int mask = [] { const char* e = getenv("RBFFD_NS2_SPECIALIZE"); return e ? atoi(e) : 3; }();
+    static bool matches(const OpTables& T, int which) {       // which: 1 = solve, 2 = elimination, 4 = column reduction kernel (bit mask in the env)
+        static const int mask = [] { const char* e = getenv("RBFFD_NS2_SPECIALIZE"); return e ? atoi(e) : 7; }();
         return NN != 0 && (mask & which) && T.n == NN && T.nops == NO;
     }
 };
@@ -1127,16 +1144,24 @@ int launch_elim(rbffd_context* ctx, Ns2Args& a) {
 template <int D, int Q, int NT, int NJ>
 int launch_solve(rbffd_context* ctx, Ns2Args& a) {
     using C = SvCfg<D, Q, NT, NJ>;
-    const size_t smem = ((size_t)(C::G + C::WT + C::SC + 64 * a.bs + 8 + C::HDR + C::XN) * 8 + 64 * 4 + 15) & ~(size_t)15;
+    using SH = Ns2Shape<D, Q, NT, NJ>;
+    using CS = SvCfg<D, Q, NT, NJ, SH::NN, SH::NO>;
+    const bool split = a.stile != nullptr && NT <= 5;
+    auto kern = split ? ns2_solve_kernel<D, Q, NT, NJ, (NT <= 5)> : ns2_solve_kernel<D, Q, NT, NJ, false>;
+    int gdoubles = C::G, btdoubles = 64 * a.bs, max_ctas = 4;
+    if constexpr (SH::NN != 0) {
+        if (split && SH::matches(a.T, 1)) {
+            kern = ns2_solve_kernel<D, Q, NT, NJ, true, SH::NN, SH::NO>;
+            gdoubles = CS::G; max_ctas = CS::MINB;
+            btdoubles = CS::BTG ? 0 : 64 * CS::BSC;
+        }
+    }
+    const size_t smem = ((size_t)(gdoubles + C::WT + C::SC + btdoubles + 8 + C::HDR + C::XN) * 8 + 64 * 4 + 15) & ~(size_t)15;
     static const int pad_smem = [] { const char* e = getenv("RBFFD_NSW_PAD_SMEM"); return e ? atoi(e) : 0; }();
     const size_t smem_launch = smem + (size_t)std::max(0, pad_smem);
     if ((int64_t)smem_launch > ctx->max_smem_optin) return RBFFD_ERR_UNSUPPORTED;
-    const bool split = a.stile != nullptr && NT <= 5;
-    auto kern = split ? ns2_solve_kernel<D, Q, NT, NJ, (NT <= 5)> : ns2_solve_kernel<D, Q, NT, NJ, false>;
-    using SH = Ns2Shape<D, Q, NT, NJ>;
-    if constexpr (SH::NN != 0) { if (split && SH::matches(a.T, 1)) kern = ns2_solve_kernel<D, Q, NT, NJ, true, SH::NN, SH::NO>; }
     CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_launch));
-    const int per_sm = std::max<int>(1, std::min<int>(4, (int)((228 * 1024) / (smem_launch + 1024))));
+    const int per_sm = std::max<int>(1, std::min<int>(max_ctas, (int)((228 * 1024) / (smem_launch + 1024))));
     static const int waves = [] { const char* e = getenv("RBFFD_NSW_WAVES"); const int w = e ? atoi(e) : 0; return w > 0 ? w : 256; }();
     const int grid = (int)std::min<int64_t>(a.cnt, (int64_t)ctx->sm_count * per_sm * waves);
 #ifdef NS2_TIMING
@@ -1180,7 +1205,12 @@ int NS2_CAT(rbffd_ns2_launch_, NS2_D, NS2_Q)(rbffd_context* ctx, Ns2Args& a) {
     {
         static const int pwaves = [] { const char* e = getenv("RBFFD_NS2_PRED_WAVES"); const int w = e ? atoi(e) : 0; return w > 0 ? w : 32; }();
         const int grid = (int)std::min<int64_t>((a.cnt + 3) / 4, (int64_t)ctx->sm_count * 4 * pwaves);
-        ns2_pred_kernel<D, Q><<<grid, 128, 0, ctx->stream>>>(a);
+        auto pk = ns2_pred_kernel<D, Q>;
+        using SH3 = Ns2Shape<D, Q, 5, 5>;
+        using SH4 = Ns2Shape<D, Q, 5, 6>;
+        if constexpr (SH3::NN != 0) { if (SH3::matches(a.T, 4)) pk = ns2_pred_kernel<D, Q, SH3::NN, SH3::NO>; }
+        if constexpr (SH4::NN != 0) { if (SH4::matches(a.T, 4)) pk = ns2_pred_kernel<D, Q, SH4::NN, SH4::NO>; }
+        pk<<<grid, 128, 0, ctx->stream>>>(a);
         KLAUNCH(ctx);
         CUDA_TRY(ctx, cudaGetLastError());
     }
