@@ -103,6 +103,7 @@ template <int D, int Q, int MINB, bool FOLD, int NN = 0, int NO = 0, int PP = 0,
 __global__ void __launch_bounds__(128, MINB) weights_ns_kernel(NArgs a) {
     constexpr int LD = NS_LD, US = NS_US;
     constexpr int KS = (Q + 3) / 4, QP = 4 * KS;      // k-steps of the DMMAs over the basic nodes
+    constexpr int PCS = (Q + 2) & ~1;                 // published pivot row of the column reduction: Q entries + 1 / pivot, even
     extern __shared__ __align__(16) unsigned char nsm[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = lane >> 2, t = lane & 3;
@@ -211,11 +212,25 @@ __global__ void __launch_bounds__(128, MINB) weights_ns_kernel(NArgs a) {
             const double rown = rcp3(prow[j]);                  // every candidate inverts its own entry under the search
             kmin = min(kmin, kmax);                             // < 32: P is rank deficient on this stencil
             const int pl = kmax & 31;
-            if (lane == pl) { basic = true; mybasic = j; }
+            // the winner publishes its row and the reciprocal of its pivot through shared memory (the Phi~ tile is idle in this
+            // phase; two buffers alternate by step parity, so one __syncwarp per step suffices): Q/2 + 1 one-lane stores and as
+            // many broadcast loads instead of 2 Q + 2 SHFLs per step
+            double* cw = G + (j & 1) * PCS;
+            if (lane == pl) {
+                basic = true; mybasic = j;
+                double2* dst = reinterpret_cast<double2*>(cw);
+#pragma unroll
+                for (int c = 0; c < PCS; c += 2) dst[c >> 1] = make_double2(c < Q ? prow[c] : rown, c + 1 < Q ? prow[c + 1] : rown);
+            }
+            __syncwarp();
             double pr[Q];
 #pragma unroll
-            for (int c = 0; c < Q; ++c) pr[c] = c == j ? 0.0 : __shfl_sync(FULL, prow[c], pl);
-            const double rinv = __shfl_sync(FULL, rown, pl);
+            for (int c = 0; c < Q; c += 2) {
+                const double2 v = reinterpret_cast<const double2*>(cw)[c >> 1];
+                pr[c] = v.x;
+                if (c + 1 < Q) pr[c + 1] = v.y;
+            }
+            const double rinv = cw[Q];
             const double tl = prow[j] * rinv;
 #pragma unroll
             for (int c = 0; c < Q; ++c)
