@@ -3,7 +3,9 @@
 
 #include <cuda_runtime.h>
 #include <cstdint>
+#include <chrono>
 #include <cstdio>
+#include <cstdlib>
 #include <string>
 #include <vector>
 
@@ -85,7 +87,14 @@ struct DevBuf {
     cudaError_t alloc(size_t count, cudaStream_t stream) {
         s = stream;
         if (count == 0) count = 1;
-        return cudaMallocAsync(reinterpret_cast<void**>(&p), count * sizeof(T), stream);
+        // RBFFD_TRACE_ALLOC=1: report pool allocations that take the host more than 1 ms (the pool growing or remapping)
+        static const bool trace = [] { const char* e = getenv("RBFFD_TRACE_ALLOC"); return e && atoi(e) != 0; }();
+        if (!trace) return cudaMallocAsync(reinterpret_cast<void**>(&p), count * sizeof(T), stream);
+        const auto t0 = std::chrono::steady_clock::now();
+        const cudaError_t e = cudaMallocAsync(reinterpret_cast<void**>(&p), count * sizeof(T), stream);
+        const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        if (ms > 1.0) fprintf(stderr, "[rbffd alloc] %.1f MB took %.2f ms on the host\n", count * sizeof(T) * 1e-6, ms);
+        return e;
     }
     T* release() { T* q = p; p = nullptr; return q; }
     ~DevBuf() { if (p) cudaFreeAsync(p, s); }
