@@ -176,8 +176,8 @@ def full_size_config(rb, ctx, torch, dev, cfg, g, peak, hbm_peak, passes=3):
 
     One untimed pass, then `passes` timed ones; the reported time of a phase is the MEDIAN over the passes and the
     individual passes are listed in `per_pass_ms`: on some boxes single passes of these multi-GB workloads stall for
-    hundreds of ms while the stream-ordered pool maps fresh physical memory (profiles/r02ah_*, r02ai_*), which has
-    nothing to do with the kernels."""
+    hundreds of ms (profiles/r02ah_fullsize_pass_variance.txt: the memory-bound binning is hit as hard as the FP64
+    kernels, other boxes show no stall at all; the cause was not pinned down, the kernels themselves are steady)."""
     dim, p, deg, n, ops = cfg["dim"], cfg["p"], cfg["polydeg"], cfg["n"], cfg["ops"]
     N = g ** dim
     r = len(ops)
