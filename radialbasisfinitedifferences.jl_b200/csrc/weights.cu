@@ -411,7 +411,7 @@ int rbffd_weights_fast(rbffd_context* ctx, const OpTables& T, const double* X, i
                        const int32_t* stencils, int32_t* colind_out, double* vals_out, int* fail_flag);
 // null-space path (weights_ns.cu): n <= 32, q <= 12; UNSUPPORTED also when a stencil fails its definiteness check
 int rbffd_weights_ns(rbffd_context* ctx, const OpTables& T, const double* X, int64_t N, const double* Y, int64_t M,
-                     const int32_t* stencils, const int32_t* center, int32_t* colind_out, double* vals_out, int* fail_flag);
+                     const int32_t* stencils, const int32_t* center, int32_t* colind_out, double* vals_out, int* fail_flag, int64_t NX = 0);
 // multi-warp null-space path (weights_nsw.cu): n <= 64, n - q <= 48; UNSUPPORTED also when a stencil fails its checks
 int rbffd_weights_nsw(rbffd_context* ctx, const OpTables& T, const double* X, int64_t N, const double* Y, int64_t M,
                       const int32_t* stencils, const int32_t* center, int32_t* colind_out, double* vals_out);
@@ -471,7 +471,7 @@ int rbffd_weights_impl(rbffd_context* ctx, const rbffd_options* opts, const doub
     // reading the stencil of the row's centre (the elimination is repeated per row: still ~8x the generic kernel's rate)
     const bool rowwise = !identity && opts->kernel != 1 && opts->kernel != 2 && opts->variant == 0;
     if (rowwise) {
-        rc = rbffd_weights_ns(ctx, T, X, M, Y, M, stencils, center, colind_out, vals_out, flags.p);
+        rc = rbffd_weights_ns(ctx, T, X, M, Y, M, stencils, center, colind_out, vals_out, flags.p, N);
         if (rc == RBFFD_ERR_UNSUPPORTED && T.n > 32) rc = rbffd_weights_ns2(ctx, T, X, M, Y, M, stencils, center, colind_out, vals_out);
         if (rc == RBFFD_ERR_UNSUPPORTED && T.n > 32) rc = rbffd_weights_nsw(ctx, T, X, M, Y, M, stencils, center, colind_out, vals_out);
         if (rc != RBFFD_OK && rc != RBFFD_ERR_UNSUPPORTED) return rc;

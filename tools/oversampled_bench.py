@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Oversampled mode (Y != X, generate_operator.jl:89-167; poisson_test.jl:56 uses M ~ 3N): weight-phase time of the generic
 kernel (one factorisation per centre, kernel=1) against the row-wise null-space kernels (default dispatch), device resident.
-usage: oversampled_bench.py [dim g over]"""
+usage: oversampled_bench.py [dim g over [lap]]   (lap: one operator, the Laplacian, instead of the reference tuple)"""
 import json, os, sys
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
 import numpy as np
@@ -12,6 +12,8 @@ dim = int(sys.argv[1]) if len(sys.argv) > 1 else 2
 g = int(sys.argv[2]) if len(sys.argv) > 2 else 1000
 over = int(sys.argv[3]) if len(sys.argv) > 3 else 3
 p, n, deg, ops = (5, 30, 3, ["E", "Dx", "Dy", "Dxx", "Dyy", "Dxy"]) if dim == 2 else (7, 60, 3, ["Lap", "Dx", "Dy", "Dz"])
+if len(sys.argv) > 4 and sys.argv[4] == "lap":
+    ops = ["Lap"]
 ctx = rb.Context(0)
 ctx.set_stream(torch.cuda.current_stream().cuda_stream)
 N = g ** dim
