@@ -58,7 +58,8 @@ typedef struct {
     int32_t index_base; /* 0 or 1: base of int64 index arrays crossing the host boundary                */
     int32_t sort_columns; /* != 0: entries of every row sorted by column (CSR form of the CSC the reference builds) */
     int32_t kernel;     /* 0 = auto, 1 = generic shared-memory LU kernel, 2 = register/DMMA Gauss-Jordan kernels,
-                           3 = null-space kernel (2 and 3: error if not applicable) */
+                           3 = null-space kernel (2 and 3: error if not applicable), 4 = as 3, but rows with Y != X are
+                           solved one by one (no sharing of the elimination between the rows of a centre) */
     int32_t variant;    /* 0 = scaled two-set methods (generate_operator.jl:29,192; hyperviscosity_operator.jl:26,177)
                            1 = legacy collocated methods generate_operator(X, p, n, polydeg) (generate_operator.jl:354) and
                                hyperviscosity_operator(K, X, p, n, polydeg) (hyperviscosity_operator.jl:314): no scaling,

@@ -467,15 +467,17 @@ int rbffd_weights_impl(rbffd_context* ctx, const rbffd_options* opts, const doub
     int rc = RBFFD_ERR_UNSUPPORTED;
     a.variant = opts->variant;
     if (opts->variant != 0 && opts->kernel > 1) RBFFD_FAIL(ctx, RBFFD_ERR_UNSUPPORTED, "the legacy collocated variant runs on the generic kernel only");
-    // Y != X (generate_operator.jl:89-167, several rows per centre): the null-space kernels run one row per work item,
-    // reading the stencil of the row's centre (the elimination is repeated per row: still ~8x the generic kernel's rate)
+    // Y != X (generate_operator.jl:89-167, several rows per centre): the single-warp null-space kernel shares one elimination
+    // between up to three rows of a centre (segmented mode, weights_ns.cu); kernel = 4 and the larger stencils run one row per
+    // work item, reading the stencil of the row's centre (the elimination is repeated per row: still ~8x the generic kernel's rate)
+    const bool want_ns = opts->kernel == 3 || opts->kernel == 4;
     const bool rowwise = !identity && opts->kernel != 1 && opts->kernel != 2 && opts->variant == 0;
     if (rowwise) {
-        rc = rbffd_weights_ns(ctx, T, X, M, Y, M, stencils, center, colind_out, vals_out, flags.p, N);
+        rc = rbffd_weights_ns(ctx, T, X, M, Y, M, stencils, center, colind_out, vals_out, flags.p, opts->kernel == 4 ? 0 : N);
         if (rc == RBFFD_ERR_UNSUPPORTED && T.n > 32) rc = rbffd_weights_ns2(ctx, T, X, M, Y, M, stencils, center, colind_out, vals_out);
         if (rc == RBFFD_ERR_UNSUPPORTED && T.n > 32) rc = rbffd_weights_nsw(ctx, T, X, M, Y, M, stencils, center, colind_out, vals_out);
         if (rc != RBFFD_OK && rc != RBFFD_ERR_UNSUPPORTED) return rc;
-        if (opts->kernel == 3 && rc != RBFFD_OK) RBFFD_FAIL(ctx, RBFFD_ERR_UNSUPPORTED, "null-space kernel not applicable (n=%d, q=%d) or a stencil failed its definiteness check", T.n, T.q);
+        if (want_ns && rc != RBFFD_OK) RBFFD_FAIL(ctx, RBFFD_ERR_UNSUPPORTED, "null-space kernel not applicable (n=%d, q=%d) or a stencil failed its definiteness check", T.n, T.q);
     }
     if (identity && opts->kernel != 1 && opts->variant == 0) {
         if (opts->kernel != 2) {
@@ -483,7 +485,7 @@ int rbffd_weights_impl(rbffd_context* ctx, const rbffd_options* opts, const doub
             if (rc == RBFFD_ERR_UNSUPPORTED && T.n > 32) rc = rbffd_weights_ns2(ctx, T, X, N, Y, M, stencils, nullptr, colind_out, vals_out);
             if (rc == RBFFD_ERR_UNSUPPORTED && T.n > 32) rc = rbffd_weights_nsw(ctx, T, X, N, Y, M, stencils, nullptr, colind_out, vals_out);
             if (rc != RBFFD_OK && rc != RBFFD_ERR_UNSUPPORTED) return rc;
-            if (opts->kernel == 3 && rc != RBFFD_OK) RBFFD_FAIL(ctx, RBFFD_ERR_UNSUPPORTED, "null-space kernel not applicable (n=%d, q=%d) or a stencil failed its definiteness check", T.n, T.q);
+            if (want_ns && rc != RBFFD_OK) RBFFD_FAIL(ctx, RBFFD_ERR_UNSUPPORTED, "null-space kernel not applicable (n=%d, q=%d) or a stencil failed its definiteness check", T.n, T.q);
         }
         if (rc == RBFFD_ERR_UNSUPPORTED) rc = rbffd_weights_fast(ctx, T, X, N, Y, M, stencils, colind_out, vals_out, flags.p);
         if (rc == RBFFD_ERR_UNSUPPORTED) rc = rbffd_weights_mw(ctx, T, X, N, Y, M, stencils, colind_out, vals_out, flags.p);

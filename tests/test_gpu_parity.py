@@ -198,6 +198,31 @@ def test_oversampled_rows_through_nullspace_kernels(ctx, oracle, d, g, p, deg, n
     assert np.array_equal(v0, v3)                                           # the automatic dispatch takes the null-space path
 
 
+@pytest.mark.parametrize("d,g,p,deg,n,ops,over", [
+    (2, 40, 5, 3, 30, ["E", "Dx", "Dy", "Dxx", "Dyy", "Dxy"], 3),          # config-2 stencil, reference tuple: 5 tile columns
+    (2, 40, 3, 3, 20, ["E", "Dx", "Dy", "Dxx", "Dyy", "Dxy"], 3),          # poisson_test.jl:52-56: 4 tile columns
+    (2, 40, 5, 3, 30, ["Lap"], 4),                                           # one operator: 3 tile columns, centres with > 3 rows
+    (2, 30, 3, 2, 14, ["Lap", "Dx"], 2),                                     # degree 2 (q = 6)
+    (3, 10, 5, 2, 30, ["Lap", "Dx", "Dy", "Dz"], 2)])                        # 3-D, degree 2 (q = 10)
+def test_segmented_rows_share_the_elimination(ctx, oracle, d, g, p, deg, n, ops, over):
+    """Y != X on the single-warp kernel: by default the rows of one centre ride as right-hand-side columns of ONE elimination
+    (generate_operator.jl:89-95,158: they share inv(A)); kernel=4 solves row by row.  Same pattern, weights equal to rounding
+    of the solve, and both within the oracle tolerance.  Clustered rows give centres with many rows, others get none."""
+    X = rb.nodes.jittered_lattice(d, g, seed=5)
+    rng = np.random.default_rng(11)
+    Y = rng.uniform(0.02, 0.98, size=(over * len(X), d))
+    Y[: len(X) // 2] = 0.3 + 0.1 * rng.uniform(size=(len(X) // 2, d))      # a cluster: up to dozens of rows per centre
+    Y[::9] = X[rng.integers(0, len(X), size=len(Y[::9]))]                   # rows exactly on a node (eta == 0)
+    cs, vs = rb.generate_raw(X, Y, p, n, deg, ops, ctx=ctx, kernel=3)
+    cr, vr = rb.generate_raw(X, Y, p, n, deg, ops, ctx=ctx, kernel=4)
+    rcol, rvals, cond = oracle.generate_operator(X, Y, p, n, deg, ops=ops, mode=0, want_cond=True)
+    center = oracle.knn(X, Y, 1)[0][:, 0]
+    assert np.array_equal(cs, rcol) and np.array_equal(cr, rcol)
+    _check_weights(vs, rvals, cond[center], ops)
+    _check_weights(vr, rvals, cond[center], ops)
+    _check_weights(vs, vr, cond[center], ops)                               # segmented vs row by row, row-wise tolerance
+
+
 def test_nullspace_kernel_falls_back_when_not_definite(ctx, oracle):
     """polydeg < (p-1)/2: Z'Phi Z is not definite, kernel=3 refuses and the automatic dispatch uses the pivoted kernels."""
     X = rb.nodes.jittered_lattice(2, 30, seed=8)
