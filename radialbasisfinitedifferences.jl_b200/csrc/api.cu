@@ -134,6 +134,7 @@ int rbffd_destroy(rbffd_context* ctx) {
     if (!ctx) return RBFFD_OK;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    dev_block_cache().clear();                    // parked temporaries go back to the pool before their streams disappear
     for (int i = 0; i < 8; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     for (int i = 0; i < 4; ++i) if (ctx->chunk_ev[i]) cudaEventDestroy(ctx->chunk_ev[i]);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);

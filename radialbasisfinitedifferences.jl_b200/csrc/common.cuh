@@ -3,7 +3,9 @@
 
 #include <cuda_runtime.h>
 #include <cstdint>
+#include <algorithm>
 #include <chrono>
+#include <mutex>
 #include <cstdio>
 #include <cstdlib>
 #include <string>
@@ -76,28 +78,101 @@ struct rbffd_operator {
         if (_rc != RBFFD_OK) return _rc; \
     } while (0)
 
-// stream-ordered temporary buffer (freed on scope exit, stream ordered)
+// Host-side free list in front of the stream-ordered pool.  cudaMallocAsync from a warm pool normally returns in microseconds,
+// but on the boxes of this pool single calls were seen to block for 50-400 ms with the pool neither growing nor short of free
+// memory (profiles/r02aq_alloc_stalls.txt) -- contention inside the driver that a library cannot fix but can stay away from:
+// temporaries go back to this list instead of cudaFreeAsync and are handed out again to requests ON THE SAME STREAM (stream
+// order makes that exactly as safe as free + malloc on that stream), so a repeated call sequence never enters the allocator.
+// RBFFD_SCRATCH_CACHE_MB bounds the bytes held (default 4096; 0 disables the list).
+struct DevBlockCache {
+    struct Blk { void* p; size_t bytes; cudaStream_t s; };
+    std::mutex mu;
+    std::vector<Blk> blks;
+    size_t held = 0, cap = 0;
+    DevBlockCache() {
+        const char* e = getenv("RBFFD_SCRATCH_CACHE_MB");
+        cap = (size_t)(e ? std::max(0ll, atoll(e)) : 4096ll) << 20;
+    }
+    void* take(size_t bytes, cudaStream_t s, size_t* got) {
+        std::lock_guard<std::mutex> lk(mu);
+        int best = -1;
+        const size_t hi = bytes + bytes / 4 + (1u << 20);
+        for (int i = 0; i < (int)blks.size(); ++i)
+            if (blks[i].s == s && blks[i].bytes >= bytes && blks[i].bytes <= hi && (best < 0 || blks[i].bytes < blks[best].bytes)) best = i;
+        if (best < 0) return nullptr;
+        void* q = blks[best].p;
+        *got = blks[best].bytes;
+        held -= blks[best].bytes;
+        blks[best] = blks.back();
+        blks.pop_back();
+        return q;
+    }
+    bool give(void* q, size_t bytes, cudaStream_t s) {
+        std::lock_guard<std::mutex> lk(mu);
+        if (held + bytes > cap) return false;
+        blks.push_back({q, bytes, s});
+        held += bytes;
+        return true;
+    }
+    // every parked block goes back to the pool (rbffd_destroy: the streams they are parked under may be about to disappear).
+    // cudaFree, not cudaFreeAsync: it needs no live stream and may not be issued while a stream capture is active anyway;
+    // blocks parked under a borrowed stream that the caller switched away from (rbffd_set_stream) simply wait here until
+    // that stream comes back or a context is destroyed.
+    void clear() {
+        std::lock_guard<std::mutex> lk(mu);
+        for (const Blk& b : blks) cudaFree(b.p);
+        blks.clear();
+        held = 0;
+    }
+};
+inline DevBlockCache& dev_block_cache() {
+    static DevBlockCache* c = new DevBlockCache();       // never destroyed: no CUDA calls during static destruction
+    return *c;
+}
+
+// stream-ordered temporary buffer (returned to the free list / the pool on scope exit, stream ordered)
 template <typename T>
 struct DevBuf {
     T* p = nullptr;
     cudaStream_t s = nullptr;
+    size_t bytes = 0;            // size of the block behind p (>= the request when it came from the free list)
+    bool parkable = false;       // allocated outside a stream capture
     DevBuf() = default;
     DevBuf(const DevBuf&) = delete;
     DevBuf& operator=(const DevBuf&) = delete;
     cudaError_t alloc(size_t count, cudaStream_t stream) {
         s = stream;
         if (count == 0) count = 1;
-        // RBFFD_TRACE_ALLOC=1: report pool allocations that take the host more than 1 ms (the pool growing or remapping)
+        const size_t want = count * sizeof(T);
+        // inside a stream capture the allocation must become a node of the graph (a parked block would be baked into the graph
+        // and handed to somebody else afterwards): no free list there
+        cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+        parkable = cudaStreamIsCapturing(stream, &cap) == cudaSuccess && cap == cudaStreamCaptureStatusNone;
+        if (parkable) {
+            if (void* q = dev_block_cache().take(want, stream, &bytes)) { p = reinterpret_cast<T*>(q); return cudaSuccess; }
+        }
+        bytes = want;
+        // RBFFD_TRACE_ALLOC=1: report pool allocations that take the host more than 1 ms
         static const bool trace = [] { const char* e = getenv("RBFFD_TRACE_ALLOC"); return e && atoi(e) != 0; }();
-        if (!trace) return cudaMallocAsync(reinterpret_cast<void**>(&p), count * sizeof(T), stream);
+        if (!trace) return cudaMallocAsync(reinterpret_cast<void**>(&p), want, stream);
         const auto t0 = std::chrono::steady_clock::now();
-        const cudaError_t e = cudaMallocAsync(reinterpret_cast<void**>(&p), count * sizeof(T), stream);
+        const cudaError_t e = cudaMallocAsync(reinterpret_cast<void**>(&p), want, stream);
         const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
-        if (ms > 1.0) fprintf(stderr, "[rbffd alloc] %.1f MB took %.2f ms on the host\n", count * sizeof(T) * 1e-6, ms);
+        if (ms > 1.0) {
+            uint64_t reserved = 0, used = 0;
+            int dev = 0;
+            cudaMemPool_t pool;
+            if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+                cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemCurrent, &reserved);
+                cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemCurrent, &used);
+            }
+            fprintf(stderr, "[rbffd alloc] %.1f MB took %.2f ms on the host (pool after: reserved %.1f MB, used %.1f MB)\n",
+                    want * 1e-6, ms, reserved * 1e-6, used * 1e-6);
+        }
         return e;
     }
     T* release() { T* q = p; p = nullptr; return q; }
-    ~DevBuf() { if (p) cudaFreeAsync(p, s); }
+    ~DevBuf() { if (p && !(parkable && dev_block_cache().give(p, bytes, s))) cudaFreeAsync(p, s); }
 };
 
 static inline int ceil_div_i64(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
