@@ -175,9 +175,9 @@ def full_size_config(rb, ctx, torch, dev, cfg, g, peak, hbm_peak, passes=3):
     """one BASELINE config at its full single-GPU size: kNN, weights, SpMV (ms per pass), both roofline fractions.
 
     One untimed pass, then `passes` timed ones; the reported time of a phase is the MEDIAN over the passes and the
-    individual passes are listed in `per_pass_ms`: on some boxes single passes of these multi-GB workloads stall for
-    hundreds of ms (profiles/r02ah_fullsize_pass_variance.txt: the memory-bound binning is hit as hard as the FP64
-    kernels, other boxes show no stall at all; the cause was not pinned down, the kernels themselves are steady)."""
+    individual passes are listed in `per_pass_ms`: on some boxes single cudaMallocAsync calls were seen to block for
+    50-400 ms (profiles/r02ah_fullsize_pass_variance.txt, r02aq_alloc_stalls.txt); the library parks its temporaries in
+    a host-side free list since then and the passes are steady -- the median and the list stay as the guard."""
     dim, p, deg, n, ops = cfg["dim"], cfg["p"], cfg["polydeg"], cfg["n"], cfg["ops"]
     N = g ** dim
     r = len(ops)
