@@ -243,6 +243,12 @@ __global__ void __launch_bounds__(128, 4) ns2_pred_kernel(Ns2Args a) {
 // ---------------------------------------------------------------------------------------------------------------------
 constexpr int SV_LD = 68;      // row stride of Phi~; == 4 (mod 16): pair stores 69 l + k, 69 l + 68 k and fragment loads 68 g + t conflict-free
 
+#ifndef NS2_PAIR_ILP
+#define NS2_PAIR_ILP 4
+#endif
+#ifndef NS2_SYM
+#define NS2_SYM 1
+#endif
 #ifndef NS2_CFG3_MINB
 #define NS2_CFG3_MINB 6
 #endif
@@ -346,6 +352,19 @@ __device__ __forceinline__ void phs_assemble_half(const double* __restrict__ Sc,
         return phs_pow_t<HP>(r2, phs_rsqrt(r2), hp);
     };
     int k = k0;
+#if NS2_PAIR_ILP >= 4
+    for (; k + 6 <= rounds; k += 8) {                       // four independent dependency chains per trip
+        int b0, b1, b2, b3;
+        const double v0 = phi(k, b0);
+        const double v1 = phi(k + 2, b1);
+        const double v2 = phi(k + 4, b2);
+        const double v3 = phi(k + 6, b3);
+        if (active) {
+            grow_l[b0] = v0; gcol_l[b0 * LD] = v0; grow_l[b1] = v1; gcol_l[b1 * LD] = v1;
+            grow_l[b2] = v2; gcol_l[b2 * LD] = v2; grow_l[b3] = v3; gcol_l[b3 * LD] = v3;
+        }
+    }
+#endif
     for (; k + 2 <= rounds; k += 4) {
         int b0, b1;
         const double v0 = phi(k, b0);
@@ -367,6 +386,7 @@ __global__ void __launch_bounds__(128, (SvCfg<D, Q, NT, NJ, NN, NO>::MINB)) ns2_
     using C = SvCfg<D, Q, NT, NJ, NN, NO>;
     static_assert(NN == 0 || SPLIT, "the shrunk Phi~ tile has no room for the exchange buffers of the in-kernel elimination");
     constexpr int LD = C::LD, KS = C::KS, US = C::US, DP = C::DP, NBP = C::NBP, JJ = C::JJ, WS = C::WS;
+    constexpr bool SYM = NN != 0 && NO != 0 && NS2_SYM != 0;      // S from the rows of the basic nodes of Y only (see phase B')
     extern __shared__ __align__(16) unsigned char wsm[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, t = lane & 3;
@@ -515,66 +535,121 @@ __global__ void __launch_bounds__(128, (SvCfg<D, Q, NT, NJ, NN, NO>::MINB)) ns2_
         if (i + gridDim.x < a.cnt) fetch_nodes();     // the next stencil's coordinates arrive under phases B .. E
         cp_async_commit();
         NS2_T(1, tid == 0);
-        // ---- B. Y = Phi~[:, N] - Phi~[:, B] W : row tiles 2*warp, 2*warp+1 (right-hand-side columns start from b, use w_p) ----
-        {
-            double cy[2][NJ][2];
-            const bool r1ok = 2 * warp + 1 < NR;
-            if (2 * warp < NR) {
-                const double* rowp[2];
-                const double* browp[2];
+        double c[NT][JJ][2];
+        if constexpr (SYM) {
+            // ---- B'. only what S = Z' Phi Z needs of Y (Phi is symmetric):  S = (Phi_NN/2 - W' T) + (Phi_NN/2 - W' T)'  with
+            //          T = Phi~[B, N] - Phi~[B, B] W / 2,  so Y is formed for the ROWS OF THE BASIC NODES only (tile rows RB0 ..,
+            //          all tile columns; the factor 1/2 rides on the W operand of the null-space columns), plus the
+            //          right-hand-side tile column JR of the other rows (b - Phi~[N, B] w_p).  Per warp: tile columns warp and
+            //          warp + 4 of the basic rows; the right-hand-side tiles of the non-basic rows go to the warps that own one
+            //          tile column only.  Everything is stored IN PLACE (row stride LD): the rows of the basic nodes and the
+            //          columns nb .. of the other rows are dead once every warp has its operands, Phi_NN stays.
+            constexpr int NB = NN - Q, RC = NJ == NT ? ((NB + 3) & ~3) : 8 * NT;
+            constexpr int RB0 = NB >> 3, NBT = C::NRT - RB0, JR = RC >> 3;
+            constexpr int W1 = NJ > 4 ? NJ - 4 : 0, NW1 = 4 - W1, NU = (RB0 + NW1 - 1) / NW1;
+            static_assert((RC & 7) + NO <= 8, "right-hand sides must sit in one tile column");
+            static_assert(8 * NJ <= (C::BTG ? NN : LD), "T rows are stored in place");
+            {
+                double cb[NBT][JJ][2], cn[NU][2];
+                const int un0 = warp - W1;                  // first right-hand-side tile of a non-basic row tile owned by this warp
 #pragma unroll
-                for (int ii = 0; ii < 2; ++ii) {
-                    const int rr = 8 * (2 * warp + ((ii == 0 || r1ok) ? ii : 0)) + g;
-                    rowp[ii] = G + rr * LD;
-                    browp[ii] = Bt + rr * BS;
-                }
-#pragma unroll
-                for (int J = 0; J < NJ; ++J)
+                for (int jj = 0; jj < JJ; ++jj) {
+                    const int J = warp + 4 * jj;
 #pragma unroll
                     for (int e = 0; e < 2; ++e) {
                         const int col = 8 * J + 2 * t + e;
-                        const bool isn = col < nb, isr = col >= rcb && col < rcb + nops;
+                        const bool isn = col < NB, isr = col >= RC && col < RC + NO, on = jj == 0 ? warp < NJ : has2;
 #pragma unroll
-                        for (int ii = 0; ii < 2; ++ii) cy[ii][J][e] = isn ? rowp[ii][col] : (isr ? browp[ii][col - rcb] : 0.0);
+                        for (int rr = 0; rr < NBT; ++rr) {
+                            const int rw = 8 * (RB0 + rr) + g;
+                            cb[rr][jj][e] = (on && isn) ? G[rw * LD + col] : ((on && isr) ? Bt[rw * BS + col - RC] : 0.0);
+                        }
                     }
+                }
+#pragma unroll
+                for (int u = 0; u < NU; ++u) {
+                    const int I = un0 + u * NW1;
+                    const bool on = un0 >= 0 && I < RB0;
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const int col = 8 * JR + 2 * t + e;
+                        cn[u][e] = (on && col >= RC && col < RC + NO) ? Bt[(8 * I + g) * BS + col - RC] : 0.0;
+                    }
+                }
 #pragma unroll
                 for (int k = 0; k < KS; ++k) {
                     const bool kin = 4 * k + t < Q;
-                    const int pc = kin ? nb + 4 * k + t : 0;
                     const double* wk = Wt + (kin ? 4 * k + t : 0) * WS + g;
-                    double af[2];
+                    const int pc = NB + (kin ? 4 * k + t : 0);
+                    double af[NBT];
 #pragma unroll
-                    for (int ii = 0; ii < 2; ++ii) af[ii] = kin ? -rowp[ii][pc] : 0.0;
+                    for (int rr = 0; rr < NBT; ++rr) af[rr] = kin ? -G[(8 * (RB0 + rr) + g) * LD + pc] : 0.0;
 #pragma unroll
-                    for (int J = 0; J < NJ; ++J) {
-                        const double bf = kin ? wk[8 * J] : 0.0;
-                        dmma884(cy[0][J][0], cy[0][J][1], af[0], bf);
-                        if (r1ok) dmma884(cy[1][J][0], cy[1][J][1], af[1], bf);
+                    for (int jj = 0; jj < JJ; ++jj) {
+                        const int J = warp + 4 * jj;
+                        if (jj == 0 ? warp < NJ : has2) {
+                            double bf = kin ? wk[8 * J] : 0.0;
+                            if (8 * J < NB) bf *= (8 * J + g < NB) ? 0.5 : 1.0;
+#pragma unroll
+                            for (int rr = 0; rr < NBT; ++rr) dmma884(cb[rr][jj][0], cb[rr][jj][1], af[rr], bf);
+                        }
+                    }
+                    if (un0 >= 0) {
+                        const double bfr = kin ? wk[8 * JR] : 0.0;
+#pragma unroll
+                        for (int u = 0; u < NU; ++u) {
+                            const int I = un0 + u * NW1;
+                            if (I < RB0) {
+                                const double afn = kin ? -G[(8 * I + g) * LD + pc] : 0.0;
+                                dmma884(cn[u][0], cn[u][1], afn, bfr);
+                            }
+                        }
+                    }
+                }
+                __syncthreads();                            // every warp has read its operands of Phi~
+#pragma unroll
+                for (int jj = 0; jj < JJ; ++jj) {
+                    const int J = warp + 4 * jj;
+                    if (jj == 0 ? warp < NJ : has2) {
+#pragma unroll
+                        for (int rr = 0; rr < NBT; ++rr) {
+                            const int rw = 8 * (RB0 + rr) + g;
+                            double* dst = G + rw * LD + 8 * J + 2 * t;
+                            if (8 * (RB0 + rr) >= NB) {         // basic rows only
+                                if (rw < NN) *reinterpret_cast<double2*>(dst) = make_double2(cb[rr][jj][0], cb[rr][jj][1]);
+                            } else {                            // mixed tile row: a non-basic row keeps its Phi_NN entries
+#pragma unroll
+                                for (int e = 0; e < 2; ++e)
+                                    if (rw < NN && (rw >= NB || 8 * J + 2 * t + e >= NB)) dst[e] = cb[rr][jj][e];
+                            }
+                        }
+                    }
+                }
+                if (un0 >= 0) {
+#pragma unroll
+                    for (int u = 0; u < NU; ++u) {
+                        const int I = un0 + u * NW1;
+                        if (I < RB0) {
+                            double* dst = G + (8 * I + g) * LD + 8 * JR + 2 * t;
+#pragma unroll
+                            for (int e = 0; e < 2; ++e)
+                                if (8 * JR + 2 * t + e >= NB) dst[e] = cn[u][e];
+                        }
                     }
                 }
             }
-            __syncthreads();                              // Phi~ is dead in every warp: the Y tile reuses its storage
-            if (2 * warp < NR) {
-#pragma unroll
-                for (int J = 0; J < NJ; ++J)
-#pragma unroll
-                    for (int ii = 0; ii < 2; ++ii)
-                        if (ii == 0 || r1ok)
-                            *reinterpret_cast<double2*>(Yb + (8 * (2 * warp + ii) + g) * US + 8 * J + 2 * t) = make_double2(cy[ii][J][0], cy[ii][J][1]);
-            }
-        }
-        __syncthreads();
-        NS2_T(2, tid == 0);
-        // ---- C. [S | t] = Y[N, :] - W' Y[B, :] : this warp owns tile columns warp and warp + 4 ----
-        double c[NT][JJ][2];
-        {
+            __syncthreads();
+            NS2_T(2, tid == 0);
+            // ---- C'. V = Phi_NN / 2 - W' T (right-hand-side columns: t = Y_N - W' Y_B as before), then S = V + V' through the tile ----
 #pragma unroll
             for (int jj = 0; jj < JJ; ++jj) {
                 const int J = warp + 4 * jj;
+                const bool on = jj == 0 ? warp < NJ : has2;
 #pragma unroll
                 for (int I = 0; I < NT; ++I) {
-                    const double2 v = (jj == 0 || has2) ? *reinterpret_cast<const double2*>(Yb + (8 * I + g) * US + 8 * J + 2 * t) : make_double2(0.0, 0.0);
-                    c[I][jj][0] = v.x; c[I][jj][1] = v.y;
+                    const double2 v = on ? *reinterpret_cast<const double2*>(G + (8 * I + g) * LD + 8 * J + 2 * t) : make_double2(0.0, 0.0);
+                    c[I][jj][0] = (8 * J + 2 * t < NB) ? 0.5 * v.x : v.x;
+                    c[I][jj][1] = (8 * J + 2 * t + 1 < NB) ? 0.5 * v.y : v.y;
                 }
             }
 #pragma unroll
@@ -585,7 +660,7 @@ __global__ void __launch_bounds__(128, (SvCfg<D, Q, NT, NJ, NN, NO>::MINB)) ns2_
 #pragma unroll
                 for (int I = 0; I < NT; ++I) af[I] = kin ? -wk[8 * I] : 0.0;
 #pragma unroll
-                for (int jj = 0; jj < JJ; ++jj) bf[jj] = (kin && (jj == 0 || has2)) ? Yb[(nb + 4 * k + t) * US + 8 * (warp + 4 * jj) + g] : 0.0;
+                for (int jj = 0; jj < JJ; ++jj) bf[jj] = (kin && (jj == 0 ? warp < NJ : has2)) ? G[(NB + 4 * k + t) * LD + 8 * (warp + 4 * jj) + g] : 0.0;
 #pragma unroll
                 for (int I = 0; I < NT; ++I) dmma884(c[I][0][0], c[I][0][1], af[I], bf[0]);
                 if constexpr (JJ > 1) {
@@ -595,19 +670,151 @@ __global__ void __launch_bounds__(128, (SvCfg<D, Q, NT, NJ, NN, NO>::MINB)) ns2_
                     }
                 }
             }
+            // V in place (this warp's own tile columns of the rows < nb: nobody else reads them in this phase)
+#pragma unroll
+            for (int jj = 0; jj < JJ; ++jj) {
+                const int J = warp + 4 * jj;
+                if ((jj == 0 ? warp < NJ : has2) && 8 * J < NB) {
+#pragma unroll
+                    for (int I = 0; I < NT; ++I) {
+                        const int rw = 8 * I + g;
+                        double* dst = G + rw * LD + 8 * J + 2 * t;
+                        if (8 * I + 8 <= NB && 8 * J + 8 <= NB) *reinterpret_cast<double2*>(dst) = make_double2(c[I][jj][0], c[I][jj][1]);
+                        else {
+#pragma unroll
+                            for (int e = 0; e < 2; ++e)
+                                if (rw < NB && 8 * J + 2 * t + e < NB) dst[e] = c[I][jj][e];
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+#pragma unroll
+            for (int jj = 0; jj < JJ; ++jj) {
+                const int J = warp + 4 * jj;
+                if ((jj == 0 ? warp < NJ : has2) && 8 * J < NB) {
+#pragma unroll
+                    for (int I = 0; I < NT; ++I) {
+                        const int rw = 8 * I + g;
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+                            const int col = 8 * J + 2 * t + e;
+                            if ((8 * I + 8 <= NB && 8 * J + 8 <= NB) || (rw < NB && col < NB)) c[I][jj][e] += G[col * LD + rw];
+                        }
+                    }
+                }
+            }
             // identity padding outside the nb x nb block; right-hand-side columns of padded rows are zero
 #pragma unroll
             for (int jj = 0; jj < JJ; ++jj) {
                 const int J = warp + 4 * jj;
 #pragma unroll
                 for (int I = 0; I < NT; ++I) {
-                    if (8 * I + 8 > nb || 8 * J + 8 > nb) {
+                    if (8 * I + 8 > NB || 8 * J + 8 > NB) {
                         const int rw = 8 * I + g;
 #pragma unroll
                         for (int e = 0; e < 2; ++e) {
                             const int col = 8 * J + 2 * t + e;
-                            if (col >= rcb) { if (rw >= nb) c[I][jj][e] = 0.0; }
-                            else if (rw >= nb || col >= nb) c[I][jj][e] = rw == col ? sgn : 0.0;
+                            if (col >= RC) { if (rw >= NB) c[I][jj][e] = 0.0; }
+                            else if (rw >= NB || col >= NB) c[I][jj][e] = rw == col ? sgn : 0.0;
+                        }
+                    }
+                }
+            }
+        } else {
+            // ---- B. Y = Phi~[:, N] - Phi~[:, B] W : row tiles 2*warp, 2*warp+1 (right-hand-side columns start from b, use w_p) ----
+            {
+                double cy[2][NJ][2];
+                const bool r1ok = 2 * warp + 1 < NR;
+                if (2 * warp < NR) {
+                    const double* rowp[2];
+                    const double* browp[2];
+    #pragma unroll
+                    for (int ii = 0; ii < 2; ++ii) {
+                        const int rr = 8 * (2 * warp + ((ii == 0 || r1ok) ? ii : 0)) + g;
+                        rowp[ii] = G + rr * LD;
+                        browp[ii] = Bt + rr * BS;
+                    }
+    #pragma unroll
+                    for (int J = 0; J < NJ; ++J)
+    #pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+                            const int col = 8 * J + 2 * t + e;
+                            const bool isn = col < nb, isr = col >= rcb && col < rcb + nops;
+    #pragma unroll
+                            for (int ii = 0; ii < 2; ++ii) cy[ii][J][e] = isn ? rowp[ii][col] : (isr ? browp[ii][col - rcb] : 0.0);
+                        }
+    #pragma unroll
+                    for (int k = 0; k < KS; ++k) {
+                        const bool kin = 4 * k + t < Q;
+                        const int pc = kin ? nb + 4 * k + t : 0;
+                        const double* wk = Wt + (kin ? 4 * k + t : 0) * WS + g;
+                        double af[2];
+    #pragma unroll
+                        for (int ii = 0; ii < 2; ++ii) af[ii] = kin ? -rowp[ii][pc] : 0.0;
+    #pragma unroll
+                        for (int J = 0; J < NJ; ++J) {
+                            const double bf = kin ? wk[8 * J] : 0.0;
+                            dmma884(cy[0][J][0], cy[0][J][1], af[0], bf);
+                            if (r1ok) dmma884(cy[1][J][0], cy[1][J][1], af[1], bf);
+                        }
+                    }
+                }
+                __syncthreads();                              // Phi~ is dead in every warp: the Y tile reuses its storage
+                if (2 * warp < NR) {
+    #pragma unroll
+                    for (int J = 0; J < NJ; ++J)
+    #pragma unroll
+                        for (int ii = 0; ii < 2; ++ii)
+                            if (ii == 0 || r1ok)
+                                *reinterpret_cast<double2*>(Yb + (8 * (2 * warp + ii) + g) * US + 8 * J + 2 * t) = make_double2(cy[ii][J][0], cy[ii][J][1]);
+                }
+            }
+            __syncthreads();
+            NS2_T(2, tid == 0);
+            // ---- C. [S | t] = Y[N, :] - W' Y[B, :] : this warp owns tile columns warp and warp + 4 ----
+            {
+    #pragma unroll
+                for (int jj = 0; jj < JJ; ++jj) {
+                    const int J = warp + 4 * jj;
+    #pragma unroll
+                    for (int I = 0; I < NT; ++I) {
+                        const double2 v = (jj == 0 || has2) ? *reinterpret_cast<const double2*>(Yb + (8 * I + g) * US + 8 * J + 2 * t) : make_double2(0.0, 0.0);
+                        c[I][jj][0] = v.x; c[I][jj][1] = v.y;
+                    }
+                }
+    #pragma unroll
+                for (int k = 0; k < KS; ++k) {
+                    const bool kin = 4 * k + t < Q;
+                    const double* wk = Wt + (kin ? 4 * k + t : 0) * WS + g;
+                    double af[NT], bf[JJ];
+    #pragma unroll
+                    for (int I = 0; I < NT; ++I) af[I] = kin ? -wk[8 * I] : 0.0;
+    #pragma unroll
+                    for (int jj = 0; jj < JJ; ++jj) bf[jj] = (kin && (jj == 0 || has2)) ? Yb[(nb + 4 * k + t) * US + 8 * (warp + 4 * jj) + g] : 0.0;
+    #pragma unroll
+                    for (int I = 0; I < NT; ++I) dmma884(c[I][0][0], c[I][0][1], af[I], bf[0]);
+                    if constexpr (JJ > 1) {
+                        if (has2) {
+    #pragma unroll
+                            for (int I = 0; I < NT; ++I) dmma884(c[I][1][0], c[I][1][1], af[I], bf[1]);
+                        }
+                    }
+                }
+                // identity padding outside the nb x nb block; right-hand-side columns of padded rows are zero
+    #pragma unroll
+                for (int jj = 0; jj < JJ; ++jj) {
+                    const int J = warp + 4 * jj;
+    #pragma unroll
+                    for (int I = 0; I < NT; ++I) {
+                        if (8 * I + 8 > nb || 8 * J + 8 > nb) {
+                            const int rw = 8 * I + g;
+    #pragma unroll
+                            for (int e = 0; e < 2; ++e) {
+                                const int col = 8 * J + 2 * t + e;
+                                if (col >= rcb) { if (rw >= nb) c[I][jj][e] = 0.0; }
+                                else if (rw >= nb || col >= nb) c[I][jj][e] = rw == col ? sgn : 0.0;
+                            }
                         }
                     }
                 }
