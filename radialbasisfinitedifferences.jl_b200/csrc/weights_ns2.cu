@@ -343,9 +343,11 @@ __device__ __forceinline__ void phs_assemble_half(const double* __restrict__ Sc,
         ib = l + k;
         ib = ib >= n ? ib - n : ib;
         double o[D];
-        const double2 v = *reinterpret_cast<const double2*>(Sc + ib * DP);
+        // (x, y) pairs at stride 16 B, z in its own array behind them: both loads are free of bank conflicts (one point per
+        // 32 B cost 8 wavefronts per load instead of 4 and 2)
+        const double2 v = *reinterpret_cast<const double2*>(Sc + ib * 2);
         o[0] = v.x; o[1] = v.y;
-        if constexpr (D == 3) o[2] = Sc[ib * DP + 2];
+        if constexpr (D == 3) o[2] = Sc[128 + ib];
         double r2 = 0.0;
 #pragma unroll
         for (int c = 0; c < D; ++c) { const double dd = me[c] - o[c]; r2 = fma(dd, dd, r2); }
@@ -452,6 +454,7 @@ __global__ void __launch_bounds__(128, (SvCfg<D, Q, NT, NJ, NN, NO>::MINB)) ns2_
         const unsigned char* rec = a.rec + i * a.rec_stride;
         cp_async_wait_all();                          // header and nodes of THIS stencil (prefetched during the previous one)
         __syncthreads();
+        NS2_T(6, tid == 0);
         // ---- 0. node phase: everything comes from shared memory ----
         const int id = reinterpret_cast<const int*>(reinterpret_cast<const unsigned char*>(hdr) + NS2_REC_PID)[P];
         double sx[D], s[D], eta[D];
@@ -466,7 +469,7 @@ __global__ void __launch_bounds__(128, (SvCfg<D, Q, NT, NJ, NN, NO>::MINB)) ns2_
             const int slot = reinterpret_cast<const unsigned char*>(hdr)[NS2_REC_PERM + P];
             perm[P] = slot;
 #pragma unroll
-            for (int c = 0; c < D; ++c) Sc[P * DP + c] = sx[c];
+            for (int c = 0; c < D; ++c) Sc[c < 2 ? 2 * P + c : 128 + P] = sx[c];
             if (P < n) {
                 G[P * LD + P] = 0.0;
                 a.colind[row * n + slot] = id;              // the pattern row in stencil order (generate_operator.jl:171-176)
@@ -488,7 +491,7 @@ __global__ void __launch_bounds__(128, (SvCfg<D, Q, NT, NJ, NN, NO>::MINB)) ns2_
             double rp4 = y;                                 // r^(p-4)
             for (int e = 1; e < hp; ++e) rp4 *= r2;
             const double rp2 = rp4 * r2, rp = rp2 * r2, r = r2 * y;
-            for (int o = tid >> 6; o < nops; o += 2) {
+            auto rhs_one = [&](const int o) {
                 int order = 0;
 #pragma unroll
                 for (int c = 0; c < D; ++c) order += T.alpha[o][c];
@@ -508,9 +511,12 @@ __global__ void __launch_bounds__(128, (SvCfg<D, Q, NT, NJ, NN, NO>::MINB)) ns2_
                     val = rhs_rbf_entry_fast<D>(T, o, del, s, r, r2, rp, rp2, rp4);
                 }
                 Bt[P * BS + o] = val;
-            }
+            };
+            // (unrolling this loop over a compile-time operator index was measured neutral: profiles/r02av)
+            for (int o = tid >> 6; o < nops; o += 2) rhs_one(o);
         }
         __syncthreads();                              // Sc complete; header and Xn are consumed
+        NS2_T(7, tid == 0);
         // W'^T of this stencil and the header of the next one stream in under the assembly
         {
             const double* Wg = reinterpret_cast<const double*>(rec + NS2_REC_W);
@@ -1381,8 +1387,8 @@ int launch_solve(rbffd_context* ctx, Ns2Args& a) {
 #ifdef NS2_TIMING
     unsigned long long h[16];
     cudaMemcpyFromSymbol(h, ns2_prof, sizeof(h));
-    static const char* nm[6] = {"0 record + nodes + rhs", "A Phi~ (4 warps)", "B Y", "C S", "D elimination", "E back+store"};
-    for (int k = 0; k < 6; ++k) fprintf(stderr, "[ns2 timing] %-26s %9.0f cycles/stencil\n", nm[k], (double)h[k] / (double)a.cnt);
+    static const char* nm[8] = {"0c W' + next header issue", "A Phi~ (4 warps)", "B Y", "C S", "D elimination", "E back+store", "0a wait for the record", "0b nodes + rhs"};
+    for (int k = 0; k < 8; ++k) fprintf(stderr, "[ns2 timing] %-26s %9.0f cycles/stencil\n", nm[k], (double)h[k] / (double)a.cnt);
 #endif
     if constexpr (NT <= 5) {
         // RBFFD_NS2_ELIM=2 keeps the two-warp elimination with its scalar panel chain (A/B comparisons)
