@@ -467,14 +467,14 @@ __global__ void __launch_bounds__(128, (SvCfg<D, Q, NT, NJ, NN, NO>::MINB)) ns2_
         }
         if (tid < 64) {
             const int slot = reinterpret_cast<const unsigned char*>(hdr)[NS2_REC_PERM + P];
-            perm[P] = slot;
+            if constexpr (!SPLIT) perm[P] = slot;           // split path: the scatter (and the chain-rule factors) belong to the elimination kernel
 #pragma unroll
             for (int c = 0; c < D; ++c) Sc[c < 2 ? 2 * P + c : 128 + P] = sx[c];
             if (P < n) {
                 G[P * LD + P] = 0.0;
                 a.colind[row * n + slot] = id;              // the pattern row in stencil order (generate_operator.jl:171-176)
             }
-            if (tid < nops) pf[tid] = op_post_factor<D>(T, tid, s);
+            if constexpr (!SPLIT) { if (tid < nops) pf[tid] = op_post_factor<D>(T, tid, s); }
         }
         if (P < n) {
             // RBF part of the right-hand sides at this node (generate_operator.jl:123-154); thread set tid/64 takes every
@@ -497,11 +497,13 @@ __global__ void __launch_bounds__(128, (SvCfg<D, Q, NT, NJ, NN, NO>::MINB)) ns2_
                 for (int c = 0; c < D; ++c) order += T.alpha[o][c];
                 double val;
                 if (a.hv_axis[o] >= 0) {                    // hyperviscosity closed form: r^(p-K) * poly((x/r)^2)
-                    const int ax = a.hv_axis[o], half = a.hv_half[o];
+                    const int ax = a.hv_axis[o];
                     const double xa = ax == 0 ? del[0] : (ax == 1 ? del[1] : del[D - 1]);
                     const double xi = xa * y, u = xi * xi;
-                    double pv = a.hv_c[o][half];
-                    for (int kk = half - 1; kk >= 0; --kk) pv = fma(pv, u, a.hv_c[o][kk]);
+                    // Horner from the top of the padded coefficient row (hv_c[o][k] == 0 for k > half): no loop, same value
+                    double pv = fma(a.hv_c[o][3], u, a.hv_c[o][2]);
+                    pv = fma(pv, u, a.hv_c[o][1]);
+                    pv = fma(pv, u, a.hv_c[o][0]);
                     double rr = r;
                     for (int e = 1; e < a.hv_rexp[o]; e += 2) rr *= r2;
                     val = rr * pv;
