@@ -175,6 +175,29 @@ def test_multiwarp_nullspace_kernel_vs_oracle(ctx, oracle, d, g, p, deg, n, ops)
     _check_weights(v3, rvals, cond, ops)
 
 
+@pytest.mark.parametrize("d,N,p,deg,n,ops", [
+    (2, 1500, 5, 4, 50, ["E", "Dx", "Dy", "Dxy"]),                          # n = 50 / four operators: the instance compiled for config 3
+    (2, 1500, 3, 4, 50, ["Lap", ("Dk", 0, 2), "Dyy", "E"]),                 # same instance, r^3
+    (3, 2500, 7, 3, 60, ["E", "Dzz", "Dxz", "Dy"]),                         # n = 60 / four operators: the instance compiled for configs 4/5
+    (3, 2500, 5, 3, 60, ["Lap", "Dxy", "Dz", "Dyy"])])                      # same instance, r^5
+def test_specialised_two_stage_instances_other_operators_scattered_nodes(ctx, oracle, d, N, p, deg, n, ops):
+    """The two-stage null-space kernels compiled for the BASELINE shapes (n = 50 or 60, four operators) are selected by (n, number of
+    operators) alone: other operator sets and PHS powers, on SCATTERED (uniformly random, locally clustered) nodes instead of a
+    jittered lattice -- in particular the symmetric form of S = Z' Phi Z (rows of the basic nodes of Y only, S = V + V')."""
+    rng = np.random.default_rng(17)
+    X = rng.random((N, d))
+    X[: N // 5] = 0.5 + 0.05 * rng.standard_normal((N // 5, d))             # a cluster: strongly varying stencil diameters
+    colind, vals = rb.generate_raw(X, None, p, n, deg, ops, ctx=ctx)
+    rcol, rvals, cond = oracle.generate_operator(X, X, p, n, deg, ops=ops, mode=0, want_cond=True)
+    assert np.array_equal(colind, rcol)
+    _check_weights(vals, rvals, cond, ops)
+    # row sums: E reproduces constants, derivatives annihilate them (polynomial reproduction of degree 0)
+    for o, nm in enumerate(ops):
+        rs = vals[o].sum(axis=1)
+        scale = np.abs(vals[o]).max(axis=1) * cond * EPS * C_TOL
+        assert np.all(np.abs(rs - (1.0 if nm == "E" else 0.0)) <= scale + 1e-12)
+
+
 @pytest.mark.parametrize("d,g,p,deg,n,ops,over", [
     (2, 40, 3, 3, 20, ["E", "Dx", "Dy", "Dxx", "Dyy", "Dxy"], 3),          # poisson_test.jl:56 (M ~ 3N), single-warp kernel
     (2, 30, 5, 5, 42, ["E", "Dx", "Dy", "Dxx", "Dyy", "Dxy"], 2),          # mesh_import_test.jl parameters, multi-warp kernel
