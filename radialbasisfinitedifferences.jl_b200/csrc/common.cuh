@@ -83,7 +83,8 @@ struct rbffd_operator {
 // memory (profiles/r02aq_alloc_stalls.txt) -- contention inside the driver that a library cannot fix but can stay away from:
 // temporaries go back to this list instead of cudaFreeAsync and are handed out again to requests ON THE SAME STREAM (stream
 // order makes that exactly as safe as free + malloc on that stream), so a repeated call sequence never enters the allocator.
-// RBFFD_SCRATCH_CACHE_MB bounds the bytes held (default 4096; 0 disables the list).
+// RBFFD_SCRATCH_CACHE_MB bounds the bytes held (default 16384: the scratch of the two-stage weight path alone is up to 12 GiB;
+// 0 disables the list).
 struct DevBlockCache {
     struct Blk { void* p; size_t bytes; cudaStream_t s; };
     std::mutex mu;
@@ -91,7 +92,7 @@ struct DevBlockCache {
     size_t held = 0, cap = 0;
     DevBlockCache() {
         const char* e = getenv("RBFFD_SCRATCH_CACHE_MB");
-        cap = (size_t)(e ? std::max(0ll, atoll(e)) : 4096ll) << 20;
+        cap = (size_t)(e ? std::max(0ll, atoll(e)) : 16384ll) << 20;
     }
     void* take(size_t bytes, cudaStream_t s, size_t* got) {
         std::lock_guard<std::mutex> lk(mu);
@@ -172,6 +173,7 @@ struct DevBuf {
         return e;
     }
     T* release() { T* q = p; p = nullptr; return q; }
+    void reset() { if (p && !(parkable && dev_block_cache().give(p, bytes, s))) cudaFreeAsync(p, s); p = nullptr; }
     ~DevBuf() { if (p && !(parkable && dev_block_cache().give(p, bytes, s))) cudaFreeAsync(p, s); }
 };
 

@@ -57,7 +57,7 @@ struct Ns2Args {
 // W'[pos][c] for the non-basic positions pos < nb and w_p[o][c] at pos = rcb + o.  Stage A's lanes (one row each, consecutive
 // lanes = consecutive positions) then store consecutive addresses, stage B copies the block into shared memory as it is, and
 // both DMMA operand loads of it (t ws + g) are free of bank conflicts for ws == 4 or 12 (mod 16).  Positions no row maps to
-// are never written: the host zero-fills the scratch buffer once.
+// are zeroed by stage A itself (the scratch buffer is recycled from call to call and never cleared by the host).
 constexpr int NS2_REC_S = 0;        // double s[3]
 constexpr int NS2_REC_XC = 24;      // double xc[3]
 constexpr int NS2_REC_ETA = 48;     // double eta[3]
@@ -232,6 +232,15 @@ __global__ void __launch_bounds__(128, 4) ns2_pred_kernel(Ns2Args a) {
         if (wrow1 >= 0) {
 #pragma unroll
             for (int c = 0; c < Q; ++c) W[c * ws + wrow1] = p1[c];
+        }
+        // positions of the W'^T block that no row maps to ([nb, rcb) and [rcb + nops, ws)) are read by stage B into padded tile
+        // rows / columns: they must be finite, so they are zeroed here (the scratch buffer is recycled, never cleared by the host)
+        {
+            const int z0 = a.rcb - nb, nz = z0 + (ws - a.rcb - nops);
+            for (int e = lane; e < Q * nz; e += 32) {
+                const int c = e / nz, z = e - c * nz;
+                W[c * ws + (z < z0 ? nb + z : a.rcb + nops + (z - z0))] = 0.0;
+            }
         }
         if (kmin < 64u && lane == 0) *a.redo = 1;
         __syncwarp();
@@ -1531,20 +1540,32 @@ int rbffd_weights_ns2(rbffd_context* ctx, const OpTables& T, const double* X, in
         const bool fold = ((nb + 3) & ~3) + T.nops <= 8 * nt;
         a.stile_stride = (split_env && nt <= 5) ? (int64_t)nt * (fold ? nt : nt + 1) * 64 : 0;
     }
-    // the scratch buffers are reused chunk by chunk (<= 1.5 GiB together)
+    // the scratch buffers are reused chunk by chunk.  Every chunk costs three launches with their tails (a solve CTA lives ~9 us,
+    // an elimination warp ~40 us), so the chunks are made as large as a budget of min(RBFFD_NS2_SCRATCH_MB = 12 GiB, an eighth of
+    // the device memory) allows: 1.5 GiB -> 12 GiB is worth 2-6 % at the BASELINE shapes (profiles/r02bi_*)
     static const int64_t chunk_env = [] { const char* e = getenv("RBFFD_NS2_CHUNK"); return e ? atoll(e) : 0ll; }();
+    static const int64_t scratch_mb = [] { const char* e = getenv("RBFFD_NS2_SCRATCH_MB"); const long long v = e ? atoll(e) : 0ll; return v > 0 ? v : 12288ll; }();
     const int64_t per_item = a.rec_stride + a.stile_stride * 8;
-    const int64_t chunk = std::min<int64_t>(M, chunk_env > 0 ? chunk_env : std::max<int64_t>(4096, ((int64_t)3 << 29) / per_item));
+    // (the device's TOTAL memory is read once per process: cudaMemGetInfo per call costs milliseconds next to a populated pool)
+    static const int64_t total_mem = [] { size_t f = 0, t = 0; return cudaMemGetInfo(&f, &t) == cudaSuccess ? (int64_t)t : (int64_t)0; }();
+    int64_t budget = scratch_mb << 20;
+    if (total_mem > 0) budget = std::min<int64_t>(budget, total_mem / 8);
+    int64_t chunk = std::min<int64_t>(M, chunk_env > 0 ? chunk_env : std::max<int64_t>(4096, budget / per_item));
     DevBuf<double> stile;
-    a.stile = nullptr;
-    if (a.stile_stride > 0) {
-        CUDA_TRY(ctx, stile.alloc((size_t)chunk * a.stile_stride, ctx->stream));
-        a.stile = stile.p;
-    }
     DevBuf<unsigned char> rec;
-    CUDA_TRY(ctx, rec.alloc((size_t)chunk * a.rec_stride, ctx->stream));
-    // positions of the W'^T block that no row maps to are read (into padded tile rows / columns) but never written
-    CUDA_TRY(ctx, cudaMemsetAsync(rec.p, 0, (size_t)chunk * a.rec_stride, ctx->stream));
+    a.stile = nullptr;
+    for (;;) {                                          // a device short of memory gets smaller chunks, not an error
+        cudaError_t e = cudaSuccess;
+        if (a.stile_stride > 0) e = stile.alloc((size_t)chunk * a.stile_stride, ctx->stream);
+        if (e == cudaSuccess) e = rec.alloc((size_t)chunk * a.rec_stride, ctx->stream);
+        if (e == cudaSuccess) break;
+        if (e != cudaErrorMemoryAllocation || chunk <= 8192) CUDA_TRY(ctx, e);
+        cudaGetLastError();
+        stile.reset();
+        rec.reset();
+        chunk = std::max<int64_t>(4096, chunk / 4);
+    }
+    if (a.stile_stride > 0) a.stile = stile.p;
     a.rec = rec.p;
     int rc = RBFFD_OK;
     for (int64_t r0 = 0; r0 < M && rc == RBFFD_OK; r0 += chunk) {
