@@ -51,15 +51,23 @@ __global__ void bbox_kernel(const double* __restrict__ X, int64_t N, int d, unsi
             hi[a] = fmax(hi[a], v);
         }
     }
+    // warp reduction, then ONE pair of atomics per axis and CTA (one per warp put 38 k atomics on six addresses at 1 M points:
+    // their serialisation in L2 was most of this kernel's 32 us)
+    __shared__ double wlo[8][3], whi[8][3];
     for (int a = 0; a < d; ++a) {
         for (int o = 16; o > 0; o >>= 1) {
             lo[a] = fmin(lo[a], __shfl_xor_sync(0xffffffffu, lo[a], o));
             hi[a] = fmax(hi[a], __shfl_xor_sync(0xffffffffu, hi[a], o));
         }
-        if ((threadIdx.x & 31) == 0) {
-            atomicMin(&mn[a], enc_double(lo[a]));
-            atomicMax(&mx[a], enc_double(hi[a]));
-        }
+        if ((threadIdx.x & 31) == 0) { wlo[(threadIdx.x >> 5) & 7][a] = lo[a]; whi[(threadIdx.x >> 5) & 7][a] = hi[a]; }
+    }
+    __syncthreads();
+    if ((int)threadIdx.x < d) {
+        const int a = threadIdx.x, nw = (blockDim.x + 31) >> 5;
+        double l = wlo[0][a], h = whi[0][a];
+        for (int w = 1; w < nw; ++w) { l = fmin(l, wlo[w][a]); h = fmax(h, whi[w][a]); }
+        atomicMin(&mn[a], enc_double(l));
+        atomicMax(&mx[a], enc_double(h));
     }
 }
 

@@ -187,14 +187,31 @@ __global__ void iota_kernel(int* p, int64_t n) {
     if (i < n) p[i] = (int)i;
 }
 
-__global__ void check_identity_kernel(const int* __restrict__ center, int64_t n, int* flag) {
-    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (i < n && center[i] != (int)i) *flag = 1;
-}
-
-__global__ void check_range_kernel(const int* __restrict__ v, int64_t n, int hi, int* flag) {
-    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (i < n && (v[i] < 0 || v[i] >= hi)) *flag = 1;
+// All index checks of one call in ONE launch: stencil ids in [0, nx) (16-byte loads when the array is aligned), centre ids in
+// [0, nctr), and whether centre is the identity.  flags[1]: centre != identity, flags[2]: an index out of range.
+__global__ void validate_indices_kernel(const int* __restrict__ st, int64_t ns, int nx, const int* __restrict__ center, int64_t m, int nctr,
+                                        int want_identity, int* flags) {
+    const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
+    bool bad = false, moved = false;
+    if (st) {
+        const bool vec = (reinterpret_cast<uintptr_t>(st) & 15) == 0;
+        const int64_t n4 = vec ? ns >> 2 : 0;
+        const int4* st4 = reinterpret_cast<const int4*>(st);
+        for (int64_t i = tid; i < n4; i += nth) {
+            const int4 v = __ldcs(st4 + i);
+            bad = bad || (unsigned)v.x >= (unsigned)nx || (unsigned)v.y >= (unsigned)nx || (unsigned)v.z >= (unsigned)nx || (unsigned)v.w >= (unsigned)nx;
+        }
+        for (int64_t i = 4 * n4 + tid; i < ns; i += nth) bad = bad || (unsigned)st[i] >= (unsigned)nx;
+    }
+    if (center) {
+        for (int64_t i = tid; i < m; i += nth) {
+            const int c = center[i];
+            bad = bad || (unsigned)c >= (unsigned)nctr;
+            moved = moved || c != (int)i;
+        }
+    }
+    if (bad) flags[2] = 1;
+    if (want_identity && moved) flags[1] = 1;
 }
 
 template <int D>
@@ -445,15 +462,15 @@ int rbffd_weights_impl(rbffd_context* ctx, const rbffd_options* opts, const doub
         rbffd_set_flags_kernel<<<1, 32, 0, st>>>(flags.p, h_flags[0], h_flags[1], h_flags[2], h_flags[3]);
     }
     struct Unhook { DevBuf<int>& f; bool on; ~Unhook() { if (on) f.p = nullptr; } } unhook{flags, deferred};
-    if (!ctx->trusted_stencils) {
-        check_range_kernel<<<ceil_div_i64(N * T.n, 256), 256, 0, st>>>(stencils, N * T.n, (int)NX, flags.p + 2);
+    if (!ctx->trusted_stencils || center) {
+        const int64_t work = std::max<int64_t>(ctx->trusted_stencils ? 0 : (N * T.n) / 4, center ? M : 0);
+        const int vb = (int)std::max<int64_t>(1, std::min<int64_t>((work + 255) / 256, (int64_t)ctx->sm_count * 16));
+        validate_indices_kernel<<<vb, 256, 0, st>>>(ctx->trusted_stencils ? nullptr : stencils, N * T.n, (int)NX, center, M, (int)N,
+                                                    center && M == N ? 1 : 0, flags.p);
         KLAUNCH(ctx);
     }
     bool identity = false;
     if (center) {
-        check_range_kernel<<<ceil_div_i64(M, 256), 256, 0, st>>>(center, M, (int)N, flags.p + 2);
-        KLAUNCH(ctx);
-        if (M == N) { check_identity_kernel<<<ceil_div_i64(M, 256), 256, 0, st>>>(center, M, flags.p + 1); KLAUNCH(ctx); }
         CUDA_TRY(ctx, rbffd_fetch_flags(ctx, flags.p, 4, h_flags));
         identity = (M == N) && h_flags[1] == 0;
     } else {
