@@ -450,8 +450,10 @@ int build_bins(rbffd_context* ctx, const double* X, int64_t N, int dim, int k_hi
     return RBFFD_OK;
 }
 
+// short_rows_dev != nullptr: the count of queries with fewer than k visible points goes to that (zeroed) device word and the
+// caller fetches it later -- several searches then share ONE status round trip instead of stalling the stream after each
 int run_knn(rbffd_context* ctx, const Bins& B, const double* Q, int64_t NQ, const int32_t* qgroup, int k,
-            int32_t* idx_out, double* d2_out) {
+            int32_t* idx_out, double* d2_out, int* short_rows_dev = nullptr) {
     cudaStream_t st = ctx->stream;
     if (NQ == 0) return RBFFD_OK;
     KnnArgs a;
@@ -468,9 +470,12 @@ int run_knn(rbffd_context* ctx, const Bins& B, const double* Q, int64_t NQ, cons
     a.idx_out = idx_out;
     a.d2_out = d2_out;
     DevBuf<int> flag;
-    CUDA_TRY(ctx, flag.alloc(1, st));
-    CUDA_TRY(ctx, cudaMemsetAsync(flag.p, 0, sizeof(int), st));
-    a.short_rows = flag.p;
+    if (short_rows_dev) a.short_rows = short_rows_dev;
+    else {
+        CUDA_TRY(ctx, flag.alloc(1, st));
+        CUDA_TRY(ctx, cudaMemsetAsync(flag.p, 0, sizeof(int), st));
+        a.short_rows = flag.p;
+    }
     size_t smem = (size_t)(KNN_BS + 1) * k * (sizeof(float) + sizeof(int));
     if ((int64_t)smem > ctx->max_smem_optin)
         RBFFD_FAIL(ctx, RBFFD_ERR_UNSUPPORTED, "k=%d needs %zu B of shared memory per block (max %d)", k, smem, ctx->max_smem_optin);
@@ -485,6 +490,7 @@ int run_knn(rbffd_context* ctx, const Bins& B, const double* Q, int64_t NQ, cons
     if (B.dim == 1) CUDA_TRY(ctx, launch(knn_kernel<1>));
     else if (B.dim == 2) CUDA_TRY(ctx, launch(knn_kernel<2>));
     else CUDA_TRY(ctx, launch(knn_kernel<3>));
+    if (short_rows_dev) return RBFFD_OK;
     int h_flag = 0;
     CUDA_TRY(ctx, cudaMemcpyAsync(&h_flag, flag.p, sizeof(int), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(ctx, cudaStreamSynchronize(st));
@@ -519,19 +525,27 @@ int rbffd_stencils_impl(rbffd_context* ctx, const double* X, int64_t N, int dim,
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev[0], st));
     RBFFD_TRY(build_bins(ctx, X, N, dim, n, xgroup, B));
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev[1], st));
-    if (stencils) RBFFD_TRY(run_knn(ctx, B, nullptr, N, nullptr, n, stencils, d2_x));
+    // both searches report into one pair of status words, fetched once behind the second launch
+    DevBuf<int> status;
+    CUDA_TRY(ctx, status.alloc(2, st));
+    CUDA_TRY(ctx, cudaMemsetAsync(status.p, 0, 2 * sizeof(int), st));
+    if (stencils) RBFFD_TRY(run_knn(ctx, B, nullptr, N, nullptr, n, stencils, d2_x, status.p));
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev[2], st));
     if (center) {
         // every Y query sees all of X (calculateneighbors.jl:90-94): unmasked search
         Bins& Bu = B;
         bool saved = Bu.has_groups;
         Bu.has_groups = false;
-        int rc = run_knn(ctx, Bu, Y, M, nullptr, 1, center, d2_y);
+        int rc = run_knn(ctx, Bu, Y, M, nullptr, 1, center, d2_y, status.p + 1);
         Bu.has_groups = saved;
         RBFFD_TRY(rc);
     }
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev[3], st));
-    CUDA_TRY(ctx, cudaEventSynchronize(ctx->ev[3]));
+    int h_status[2] = {0, 0};
+    CUDA_TRY(ctx, cudaMemcpyAsync(h_status, status.p, sizeof(h_status), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(ctx, cudaStreamSynchronize(st));
+    if (h_status[0] > 0) RBFFD_FAIL(ctx, RBFFD_ERR_K_TOO_LARGE, "%d queries see fewer than k=%d points", h_status[0], n);
+    if (h_status[1] > 0) RBFFD_FAIL(ctx, RBFFD_ERR_K_TOO_LARGE, "%d queries see fewer than k=%d points", h_status[1], 1);
     float ms;
     for (int i = 0; i < 3; ++i) {
         CUDA_TRY(ctx, cudaEventElapsedTime(&ms, ctx->ev[i], ctx->ev[i + 1]));
