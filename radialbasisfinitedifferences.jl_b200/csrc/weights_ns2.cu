@@ -15,6 +15,12 @@
 //            are contiguous and conflict-free (the permuted gather cost 11 % of the samples before); S, the elimination
 //            and the back substitution work on tiles sized for the stencil at hand (NT = ceil(nb/8) row tiles, NJ
 //            tile columns) instead of the fixed 48 x 56 padding.
+//            The instances compiled for the BASELINE shapes form S from the rows of the basic nodes of Y only:
+//            S = V + V',  V = Phi~[N,N]/2 - W' T,  T = Phi~[B,N] - Phi~[B,B] W / 2  (Phi is symmetric), stored in place in the
+//            Phi~ tile -- about half the DMMAs of the Y phase (phase B' / C' of ns2_solve_kernel).
+//   stage C  ns2_elim1_kernel  ONE WARP per stencil: [S | t] register-resident from the load to the last pivot, unpivoted
+//            Gauss-Jordan by 4 x 4 block pivots (nullspace.cuh), back substitution and the CSR row.
+//   The three stages work through the rows in chunks sized by a scratch budget (min(12 GiB, 1/8 of the device memory)).
 //
 // Compiled once per (dimension, monomial count): -DNS2_D=<d> -DNS2_Q=<q> emits the kernels and
 // rbffd_ns2_launch_<d>_<q>; without those macros the file emits the dispatcher rbffd_weights_ns2.
